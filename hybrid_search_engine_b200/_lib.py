@@ -1,0 +1,90 @@
+"""ctypes binding of the C-ABI library ``libhs_b200.so`` (include/hs_b200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises.  PyTorch is used only
+for device memory, streams and ``torch.distributed`` -- tensors go in as raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch  # noqa: F401  (loads libcudart before our library so both share one runtime)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhs_b200.so")
+
+HS_DENSE_EXACT, HS_DENSE_FP32, HS_DENSE_BF16 = 0, 1, 2
+HS_FUSE_RAW, HS_FUSE_SEARCHER, HS_FUSE_HYBRID_BM25 = 0, 1, 2
+HS_TOPK_MAX = 2048
+DENSE_MODES = {"exact": HS_DENSE_EXACT, "fp32": HS_DENSE_FP32, "bf16": HS_DENSE_BF16}
+
+_vp, _i32, _i64, _u32, _u64, _f64, _sz = (C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64,
+                                          C.c_double, C.c_size_t)
+
+# name -> (restype, argtypes); must list every symbol include/hs_b200.h declares
+SIGNATURES = {
+    "hs_abi_version": (C.c_int, []),
+    "hs_last_error": (C.c_char_p, []),
+    "hs_index_create": (C.c_int, [C.c_int, _i64, _i64, C.POINTER(_vp)]),
+    "hs_index_destroy": (C.c_int, [_vp]),
+    "hs_index_set_dense": (C.c_int, [_vp, _vp, _i32, _i64, _vp]),
+    "hs_index_set_csr": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),
+    "hs_index_set_doc_stats": (C.c_int, [_vp, _vp, _f64, _f64, _f64, _vp, _u32]),
+    "hs_row_norms": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp]),
+    "hs_bm25_kd_table": (C.c_int, [_f64, _f64, _f64, _u32, _vp, _vp]),
+    "hs_stats_reset": (C.c_int, [_vp, _i32, _vp]),
+    "hs_stats_decode": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "hs_stats_encode": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "hs_stats_fold_minmax": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+    "hs_dense_scan": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "hs_bm25_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "hs_fuse_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "hs_fuse_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),
+    "hs_topk_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "hs_keys_unpack": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
+    "hs_mmr_workspace_bytes": (_sz, [_i32, _i32]),
+    "hs_mmr": (C.c_int, [_vp, _vp, _vp, _f64, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
+    "hs_synth_embeddings": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _u64, _vp]),
+    "hs_synth_doc_lengths": (C.c_int, [_vp, _i64, _i64, _u64, _u32, _u32, _vp]),
+    "hs_synth_token_keys": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _u64, _vp, _i32, _vp]),
+}
+
+_lib = None
+
+
+class HsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library (once).  Raises if it has not been built -- there is no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HsError(
+            f"{LIB_PATH} is missing: build it with `python -m hybrid_search_engine_b200.build_native` "
+            "(or __graft_entry__.build()). The hot path has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().hs_last_error().decode("utf-8", "replace")
+        raise HsError(f"{what or 'hs call'} failed (status {rc}): {msg}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream

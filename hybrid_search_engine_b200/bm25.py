@@ -1,0 +1,109 @@
+"""``BM25`` -- mirror of the reference's bm25.py API with the scoring on the device.
+
+``fit`` tokenises on the host (term identity, bm25.py:58-67) and uploads a CSR inverted index;
+``score`` / ``score_batch`` / ``search`` run the hs_b200 BM25 kernels.  ``BM25Okapi`` is the same class
+(bm25.py:145-147).  ``BM25Plus`` (bm25.py:150-179) is dense (every doc gets ``idf * delta`` per known
+query term) and is used by no pipeline; it is not part of this round's device path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import QueryBatch, SearchEngine
+from .index import DeviceIndex, LexicalStats
+
+
+class BM25:
+    def __init__(self, k1: float = 1.5, b: float = 0.75, remove_stopwords: bool = True, *, device=None):
+        self.k1 = k1
+        self.b = b
+        self.remove_stopwords = remove_stopwords
+        self._device = device
+        self.stats = LexicalStats(remove_stopwords)
+        self.shard: Optional[DeviceIndex] = None
+        self.engine: Optional[SearchEngine] = None
+        self.doc_count = 0
+        self.avg_doc_len = 0.0
+        self.doc_lengths: List[int] = []
+
+    # ---- corpus statistics in the reference's shapes (built lazily, host side) -----------------
+    @property
+    def doc_freqs(self) -> Dict[str, int]:
+        return {t: int(self.stats.df[i]) for t, i in self.stats.vocab.items()}
+
+    @property
+    def idf(self) -> Dict[str, float]:
+        if self.shard is None or self.shard.idf_host is None:
+            return {}
+        return {t: float(self.shard.idf_host[i]) for t, i in self.stats.vocab.items()}
+
+    def fit(self, documents: Sequence[str], *, shard: Optional[DeviceIndex] = None):
+        """bm25.py:45-81.  ``shard``: attach to an existing device shard (the pipeline's dense one)."""
+        st = self.stats = LexicalStats(self.remove_stopwords).fit(documents)
+        self.doc_count = st.doc_count
+        self.avg_doc_len = st.avg_doc_len
+        self.doc_lengths = st.doc_lengths.tolist()
+        if st.doc_count == 0:
+            self.shard = self.engine = None
+            return
+        if not torch.cuda.is_available():
+            raise _lib.HsError("no CUDA device: BM25 scoring has no CPU fallback")
+        if shard is None:
+            dev = torch.device(self._device) if self._device is not None else \
+                torch.device("cuda", torch.cuda.current_device())
+            shard = DeviceIndex(dev, st.doc_count)
+        self.shard = shard
+        shard.set_bm25(torch.from_numpy(st.indptr), torch.from_numpy(st.postings.view(np.int32)),
+                       torch.from_numpy(st.doc_lengths.astype(np.uint32).view(np.int32)), float(st.avg_doc_len),
+                       st.df, st.doc_count, self.k1, self.b)
+        self.engine = SearchEngine(shard)
+
+    # ---- scoring --------------------------------------------------------------------------------
+    def score_batch_many(self, queries: Sequence[str]) -> np.ndarray:
+        """float32 [B, N] BM25 scores (bm25.py:114-127 for a batch of queries)."""
+        if self.doc_count == 0:
+            return np.zeros((len(queries), 0), np.float32)
+        eng = self.engine
+        terms = [self.stats.query_term_ids(q) for q in queries]
+        with torch.cuda.device(eng.device):
+            qt, qi, qo = eng.upload_terms(terms)
+            sc = eng.bm25_score(qt, qi, qo, len(queries), None)
+            return sc.cpu().numpy()
+
+    def score_batch(self, query: str) -> np.ndarray:
+        return self.score_batch_many([query])[0]
+
+    def score(self, query: str, doc_idx: int) -> float:
+        """bm25.py:83-112 -- float64, unrounded."""
+        if doc_idx < 0:
+            doc_idx += self.doc_count
+        if not 0 <= doc_idx < self.doc_count:
+            raise IndexError("list index out of range")
+        eng = self.engine
+        ids = torch.tensor([[doc_idx]], dtype=torch.int64, device=eng.device)
+        return float(eng.bm25_score_docs([self.stats.query_term_ids(query)], ids).cpu()[0, 0])
+
+    def search_many(self, queries: Sequence[str], top_k: int = 10) -> List[List[tuple]]:
+        """bm25.py:129-142 per query -> [(doc_idx, score)], canonical order (score desc, doc_idx asc)."""
+        if self.doc_count == 0:
+            return [[] for _ in queries]
+        n = self.doc_count
+        k = min(int(top_k), n) if top_k >= 0 else max(n + int(top_k), 0)
+        if k == 0:
+            return [[] for _ in queries]
+        qb = QueryBatch(term_ids=[self.stats.query_term_ids(q) for q in queries])
+        sc, ids = self.engine.search_bm25(qb, k)
+        sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
+        return [[(int(i), float(s)) for s, i in zip(sc[q], ids[q]) if i >= 0] for q in range(len(queries))]
+
+    def search(self, query: str, top_k: int = 10) -> List[tuple]:
+        return self.search_many([query], top_k)[0]
+
+
+class BM25Okapi(BM25):
+    """bm25.py:145-147."""
+    pass

@@ -1,0 +1,167 @@
+"""``Searcher`` -- mirror of the reference's core.py:112-285 for the hot path.
+
+``Searcher.search(query, docs_df, vectors, top_k, semantic_weight, lexical_weight)`` keeps the
+reference's signature, defaults (0.7 / 0.3, core.py:229-230), weight check (core.py:232-233) and
+return type ``[(float score, content, doc_id)]``; the arithmetic (cosine scan, min-max, weighted
+sum, top-k) runs in the hs_b200 kernels.  QueryMemory / DuckDB logging (core.py:20-109,280-281) is
+bookkeeping outside the hot path and is not performed.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import QueryBatch, SearchEngine
+from .index import DeviceIndex
+
+
+class _Column:
+    def __init__(self, values):
+        self._values = values
+
+    def to_list(self):
+        return list(self._values)
+
+    def __len__(self):
+        return len(self._values)
+
+    def __getitem__(self, i):
+        return self._values[i]
+
+
+class DocTable:
+    """The two columns of the reference's polars frame the hot path reads (core.py:240-241):
+    ``table['content'].to_list()`` and ``table['doc_id'].to_list()``; doc_id == row (indexer.py:220)."""
+
+    def __init__(self, contents: Sequence[str]):
+        self.contents = list(contents)
+
+    def __getitem__(self, col):
+        if col == "content":
+            return _Column(self.contents)
+        if col == "doc_id":
+            return _Column(range(len(self.contents)))
+        raise KeyError(col)
+
+    def __len__(self):
+        return len(self.contents)
+
+
+def default_encoder():
+    """The reference hard-wires SentenceTransformer('all-MiniLM-L6-v2') (core.py:134, indexer.py:91)."""
+    try:
+        from sentence_transformers import SentenceTransformer
+    except ImportError as e:
+        raise ImportError(
+            "no encoder given and sentence-transformers is not installed; pass encoder= (an object with "
+            "encode(list[str]) -> float32 [n, d]) or precomputed embeddings / query vectors") from e
+    return SentenceTransformer("all-MiniLM-L6-v2")
+
+
+class CrossEncoderReranker:
+    """Stage-3 hook of multi_stage (reranker.py:50-89): scores (query, content) pairs with an external
+    model and re-sorts.  Transformer inference is outside the hot path; ``predict`` is injectable."""
+
+    def __init__(self, model_name: str = "cross-encoder/ms-marco-MiniLM-L-6-v2", device=None, predict=None):
+        self.model_name = model_name
+        self._predict = predict
+        self._device = device
+
+    def rerank(self, query: str, results, top_k: Optional[int] = None):
+        if not results:
+            return results
+        if self._predict is None:
+            try:
+                from sentence_transformers import CrossEncoder
+            except ImportError as e:
+                raise ImportError("multi_stage stage 3 needs a cross-encoder: pass reranker= to the pipeline "
+                                  "or install sentence-transformers") from e
+            model = CrossEncoder(self.model_name, device=self._device)
+            self._predict = lambda pairs: model.predict(pairs, show_progress_bar=False)
+        scores = self._predict([(query, content) for _, content, _ in results])
+        ranked = [(float(s), c, d) for s, (_, c, d) in zip(scores, results)]
+        ranked.sort(key=lambda x: x[0], reverse=True)
+        return ranked[:top_k] if top_k else ranked
+
+
+class Searcher:
+    """core.py:112-285.  Holds the device shard for the (docs_df, vectors) it was last given."""
+
+    def __init__(self, model_name: str = "all-MiniLM-L6-v2", db_path: str = "index.duckdb", use_faiss: bool = False,
+                 faiss_index_path: str = "index.faiss", enable_query_memory: bool = True, *, encoder=None,
+                 device=None, dense_mode: str = "exact", lexical_scorer=None):
+        if use_faiss:
+            raise NotImplementedError("use_faiss=True (core.py:159-168) is not on the pipeline path")
+        self.model = encoder
+        self.db_path = db_path
+        self.use_faiss = False
+        self.query_memory = None
+        self._device = device
+        self._dense_mode = dense_mode
+        self._lexical_scorer = lexical_scorer
+        self.shard: Optional[DeviceIndex] = None
+        self.engine: Optional[SearchEngine] = None
+        self._attached = None
+
+    # ------------------------------------------------------------------
+    def attach(self, docs_df, vectors: np.ndarray):
+        """Upload ``vectors`` (float32 [N, d], indexer.py:285) once; later searches reuse the shard."""
+        key = (id(docs_df), id(vectors), getattr(vectors, "shape", None))
+        if self._attached == key:
+            return
+        if not torch.cuda.is_available():
+            raise _lib.HsError("no CUDA device: the hybrid scoring path has no CPU fallback")
+        dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
+        vectors = np.ascontiguousarray(vectors, dtype=np.float32)
+        n = vectors.shape[0]
+        self.shard = DeviceIndex(dev, n)
+        if n > 0:
+            self.shard.set_dense(torch.from_numpy(vectors).to(dev))
+        else:
+            self.shard.dim = vectors.shape[1] if vectors.ndim == 2 else 0
+        self.engine = SearchEngine(self.shard, dense_mode=self._dense_mode)
+        self._attached = key
+
+    def _lexical_scores(self, query: str, docs: List[str]) -> np.ndarray:
+        """core.py:178-197 (rapidfuzz partial_ratio + token overlap)."""
+        if self._lexical_scorer is None:
+            from .lexical import LexicalScorer
+            self._lexical_scorer = LexicalScorer(self.shard.device)
+        return self._lexical_scorer.scores(query, docs)
+
+    def search(self, query: str, docs_df, vectors: np.ndarray, top_k: int = 5,
+               semantic_weight: Optional[float] = None, lexical_weight: Optional[float] = None,
+               use_learned_weights: bool = False, *, query_vector=None) -> List[Tuple[float, str, int]]:
+        if use_learned_weights:
+            raise NotImplementedError("learned weights need QueryMemory/DuckDB (core.py:224-226): out of scope")
+        semantic_weight = semantic_weight if semantic_weight is not None else 0.7
+        lexical_weight = lexical_weight if lexical_weight is not None else 0.3
+        if not np.isclose(semantic_weight + lexical_weight, 1.0):
+            raise ValueError("semantic_weight and lexical_weight must sum to 1.0")
+        self.attach(docs_df, vectors)
+        docs = docs_df["content"].to_list()
+        doc_ids = docs_df["doc_id"].to_list()
+        n = len(docs)
+        if n == 0:
+            # utils.py:67 on an empty array
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")
+        if query_vector is None:
+            if self.model is None:
+                self.model = default_encoder()
+            query_vector = self.model.encode([query])[0]
+        q = np.asarray(query_vector, dtype=np.float32)[None, :]
+        k = min(int(top_k), n) if top_k >= 0 else max(n + int(top_k), 0)
+        if k == 0:
+            return []
+        eng = self.engine
+        if lexical_weight == 0.0:
+            # lex_norm * 0.0 == +0.0 for every finite lexical vector (core.py:268): skip computing it
+            sc, ids = eng.search_semantic(QueryBatch(vectors=q), k, semantic_weight)
+        else:
+            lex = self._lexical_scores(query, docs)
+            sc, ids = eng.search_searcher(QueryBatch(vectors=q), lex[None, :], k, semantic_weight, lexical_weight)
+        sc, ids = sc.cpu().numpy()[0], ids.cpu().numpy()[0]
+        return [(float(s), docs[int(i)], doc_ids[int(i)]) for s, i in zip(sc, ids) if i >= 0]

@@ -1,0 +1,277 @@
+// K1 -- BM25 scoring over a device-resident CSR inverted index (replaces bm25.py:83-127
+// BM25.score / score_batch, called from pipelines.py:271,328,485).
+//
+// Design (doc-range tiles, no global atomics, no score buffer round trip through HBM during
+// accumulation):
+//   * grid = (doc tiles, queries).  A CTA owns kTileDocs consecutive docs and keeps their float64
+//     partial scores in shared memory; the tile's doc lengths are staged into shared memory once
+//     (coalesced) -- the "document-length table staged in shared memory" of the north star.
+//   * for each query token IN QUERY ORDER (bm25.py:99, duplicates included) the CTA locates the
+//     slice of that term's posting list that falls in its doc range (warp-wide 32-ary search on the
+//     ascending doc ids), then streams the slice with coalesced 8-byte (doc_id, tf) loads.  A doc
+//     occurs at most once per posting list, so `acc[doc] += contribution` is a plain shared-memory
+//     read-modify-write; __syncthreads() between tokens keeps the reference's float64 summation order.
+//   * arithmetic is the reference's, float64, no FMA contraction (bm25.py:104-110):
+//         num = tf * (k1 + 1); den = tf + k1 * (1 - b + b * (dl / avgdl)); score += idf * (num / den)
+//     k1 * (...) depends on dl only and comes from a float64 table indexed by dl (hs_bm25_kd_table),
+//     or is computed inline when no table was given.
+//   * epilogue: single rounding to float32 (bm25.py:124-126), coalesced store, tile max folded into
+//     stats slot HS_STAT_MAX_B (pipelines.py:332).
+//
+// Algorithmic bytes per query: 8 * P(q) postings + 4 * N doc lengths + 4 * N score store.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileDocs = 4096;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kTermGroup = 32;   // query tokens resolved per search round
+
+struct Bm25Params {
+    const int64_t* indptr;
+    const uint2* postings;
+    const uint32_t* dl;
+    const double* kd_table;
+    uint32_t max_dl;
+    double k1, one_minus_b, b, avgdl, k1p1;
+    const int32_t* q_terms;
+    const double* q_idf;
+    const int32_t* q_off;
+    int64_t n_docs, n_terms;
+    float* scores;        // [B, n]
+    uint32_t* stats;      // [B, 4] or null
+};
+
+__device__ __forceinline__ double bm25_kd(const Bm25Params& p, uint32_t dl) {
+    if (p.kd_table != nullptr && dl <= p.max_dl) return __ldg(p.kd_table + dl);
+    // k1 * (1 - b + b * (dl / avgdl))   (bm25.py:108)
+    return __dmul_rn(p.k1, __dadd_rn(p.one_minus_b, __dmul_rn(p.b, __ddiv_rn((double)dl, p.avgdl))));
+}
+
+// first index in [lo, hi) whose doc id >= target; whole warp cooperates (32-ary search)
+__device__ __forceinline__ int64_t warp_lower_bound(const uint2* __restrict__ post, int64_t lo, int64_t hi,
+                                                    uint32_t target, int lane) {
+    while (hi - lo > 32) {
+        const int64_t step = (hi - lo + 31) / 32;
+        // probe positions lo + (lane+1)*step - 1, clamped
+        int64_t pos = lo + (int64_t)(lane + 1) * step - 1;
+        if (pos >= hi) pos = hi - 1;
+        const bool ge = __ldg(&post[pos].x) >= target;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, ge);
+        if (m == 0) {
+            lo = hi;   // every probe (the last is hi-1) is < target
+            break;
+        }
+        const int f = __ffs(m) - 1;   // first probe that is >= target
+        int64_t new_hi = lo + (int64_t)(f + 1) * step - 1;
+        if (new_hi >= hi) new_hi = hi - 1;
+        const int64_t new_lo = lo + (int64_t)f * step;   // everything before probe f-1 (incl.) is < target
+        lo = new_lo;
+        hi = new_hi + 1;   // answer is in [new_lo, new_hi]
+        if (hi - lo <= 32) break;
+    }
+    // final: <= 32 candidates
+    const int64_t pos = lo + lane;
+    const bool ge = (pos < hi) ? (__ldg(&post[pos].x) >= target) : true;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, ge);
+    const int f = __ffs(m) - 1;
+    int64_t r = lo + f;
+    return r < hi ? r : hi;
+}
+
+__global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p) {
+    extern __shared__ __align__(16) unsigned char bm25_smem[];
+    double* acc = reinterpret_cast<double*>(bm25_smem);                       // [kTileDocs] float64 partial scores
+    uint32_t* sdl = reinterpret_cast<uint32_t*>(acc + kTileDocs);             // [kTileDocs] staged doc lengths
+    __shared__ int64_t rng_lo[kTermGroup], rng_hi[kTermGroup];
+    __shared__ double s_idf[kTermGroup];
+    __shared__ float warp_max[kWarps];
+    __shared__ int s_any;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int64_t d_lo = (int64_t)blockIdx.x * kTileDocs;
+    const int64_t d_hi = (d_lo + kTileDocs < p.n_docs) ? d_lo + kTileDocs : p.n_docs;
+    const int ndoc = (int)(d_hi - d_lo);
+    const int t_begin = p.q_off[b], t_end = p.q_off[b + 1];
+
+    for (int j = tid; j < ndoc; j += kThreads) acc[j] = 0.0;
+    bool dl_staged = false;
+
+    for (int g0 = t_begin; g0 < t_end; g0 += kTermGroup) {
+        const int gn = (t_end - g0 < kTermGroup) ? (t_end - g0) : kTermGroup;
+        if (tid == 0) s_any = 0;
+        __syncthreads();
+        // ---- locate each token's posting slice for this doc range (one warp per token)
+        for (int t = warp; t < gn; t += kWarps) {
+            const int term = p.q_terms[g0 + t];
+            int64_t lo = 0, hi = 0;
+            if (term >= 0 && term < p.n_terms) {
+                const int64_t pl = p.indptr[term], ph = p.indptr[term + 1];
+                lo = warp_lower_bound(p.postings, pl, ph, (uint32_t)d_lo, lane);
+                hi = (d_hi >= p.n_docs) ? ph : warp_lower_bound(p.postings, lo, ph, (uint32_t)d_hi, lane);
+            }
+            if (lane == 0) {
+                rng_lo[t] = lo;
+                rng_hi[t] = hi;
+                s_idf[t] = p.q_idf[g0 + t];
+                if (hi > lo) s_any = 1;
+            }
+        }
+        __syncthreads();
+        if (!s_any) continue;
+        if (!dl_staged) {
+            for (int j = tid; j < ndoc; j += kThreads) sdl[j] = p.dl[d_lo + j];
+            dl_staged = true;
+            __syncthreads();
+        }
+        // ---- accumulate token by token, in query order
+        for (int t = 0; t < gn; ++t) {
+            const int64_t lo = rng_lo[t], hi = rng_hi[t];
+            const double idf = s_idf[t];
+            for (int64_t i = lo + tid; i < hi; i += kThreads) {
+                const uint2 pt = __ldg(&p.postings[i]);
+                const int j = (int)(pt.x - (uint32_t)d_lo);
+                const double tf = (double)pt.y;
+                const double num = __dmul_rn(tf, p.k1p1);
+                const double den = __dadd_rn(tf, bm25_kd(p, sdl[j]));
+                if (den > 0.0) acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, __ddiv_rn(num, den)));
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+
+    // ---- epilogue: float64 -> float32 once, store, tile max
+    float mx = 0.0f;
+    float* out = p.scores + (int64_t)b * p.n_docs + d_lo;
+    for (int j = tid; j < ndoc; j += kThreads) {
+        const float s = __double2float_rn(acc[j]);
+        out[j] = s;
+        mx = fmaxf(mx, s);
+    }
+    if (p.stats != nullptr) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+        if (lane == 0) warp_max[warp] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            float v = warp_max[0];
+            for (int w = 1; w < kWarps; ++w) v = fmaxf(v, warp_max[w]);
+            atomicMax(&p.stats[b * 4 + HS_STAT_MAX_B], hs_enc_f32(v));
+        }
+    }
+}
+
+__global__ void kd_table_kernel(double avgdl, double k1, double one_minus_b, double b, uint32_t max_dl,
+                                double* kd) {
+    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l <= max_dl)
+        kd[l] = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, __ddiv_rn((double)l, avgdl))));
+}
+
+// BM25.score for selected docs (multi_stage stage 2, pipelines.py:485): one warp per (query, candidate);
+// per token a 32-ary search of the posting list for the doc, float64 accumulation in query order.
+__global__ void bm25_docs_kernel(const Bm25Params p, const int64_t* __restrict__ doc_ids, int C,
+                                 double* __restrict__ out, int B) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (int64_t)B * C) return;
+    const int b = (int)(w / C);
+    const int64_t doc = doc_ids[w];
+    double score = 0.0;
+    if (doc >= 0 && doc < p.n_docs) {
+        const double kd = bm25_kd(p, p.dl[doc]);
+        for (int t = p.q_off[b]; t < p.q_off[b + 1]; ++t) {
+            const int term = p.q_terms[t];
+            if (term < 0 || term >= p.n_terms) continue;
+            const int64_t pl = p.indptr[term], ph = p.indptr[term + 1];
+            const int64_t pos = warp_lower_bound(p.postings, pl, ph, (uint32_t)doc, lane);
+            if (pos < ph) {
+                const uint2 pt = __ldg(&p.postings[pos]);
+                if (pt.x == (uint32_t)doc) {
+                    const double tf = (double)pt.y;
+                    const double num = __dmul_rn(tf, p.k1p1);
+                    const double den = __dadd_rn(tf, kd);
+                    if (den > 0.0) score = __dadd_rn(score, __dmul_rn(p.q_idf[t], __ddiv_rn(num, den)));
+                }
+            }
+        }
+    }
+    if (lane == 0) out[w] = score;
+}
+
+int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                Bm25Params& p, const char* who) {
+    if (idx->indptr == nullptr || idx->dl == nullptr) {
+        hs_set_error("%s: index has no CSR / doc stats (call hs_index_set_csr and hs_index_set_doc_stats)", who);
+        return HS_ERR_STATE;
+    }
+    HS_REQUIRE(q_terms != nullptr && q_idf != nullptr && q_off != nullptr, "%s: null query arrays", who);
+    p.indptr = idx->indptr;
+    p.postings = idx->postings;
+    p.dl = idx->dl;
+    p.kd_table = idx->kd_table;
+    p.max_dl = idx->max_dl;
+    p.k1 = idx->k1;
+    p.b = idx->b;
+    p.one_minus_b = 1 - idx->b;          // python: 1 - self.b
+    p.k1p1 = idx->k1 + 1;                // python: self.k1 + 1
+    p.avgdl = idx->avgdl;
+    p.q_terms = q_terms;
+    p.q_idf = q_idf;
+    p.q_off = q_off;
+    p.n_docs = idx->n_docs;
+    p.n_terms = idx->n_terms;
+    p.scores = nullptr;
+    p.stats = nullptr;
+    return HS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hs_bm25_kd_table(double avgdl, double k1, double b, uint32_t max_dl, double* kd, void* stream) {
+    HS_REQUIRE(kd != nullptr, "hs_bm25_kd_table: kd is null");
+    const uint32_t n = max_dl + 1;
+    kd_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(avgdl, k1, 1 - b, b, max_dl, kd);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+
+int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                  int32_t B, float* scores, uint32_t* stats_enc, void* stream) {
+    HS_REQUIRE(idx != nullptr, "hs_bm25_score: idx is null");
+    if (idx->n_docs == 0 || B == 0) return HS_OK;
+    HS_REQUIRE(B > 0 && B <= 65535 && scores != nullptr, "hs_bm25_score: bad arguments (B=%d)", B);
+    Bm25Params p;
+    int rc = fill_params(idx, q_terms, q_idf, q_off, p, "hs_bm25_score");
+    if (rc != HS_OK) return rc;
+    p.scores = scores;
+    p.stats = stats_enc;
+    dim3 grid((unsigned)((idx->n_docs + kTileDocs - 1) / kTileDocs), (unsigned)B);
+    const size_t smem = (size_t)kTileDocs * (sizeof(double) + sizeof(uint32_t));
+    HS_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bm25_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+
+int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                       int32_t B, const int64_t* doc_ids, int32_t C, double* out, void* stream) {
+    HS_REQUIRE(idx != nullptr, "hs_bm25_score_docs: idx is null");
+    if (B == 0 || C == 0) return HS_OK;
+    HS_REQUIRE(B > 0 && C > 0 && doc_ids != nullptr && out != nullptr, "hs_bm25_score_docs: bad arguments");
+    Bm25Params p;
+    int rc = fill_params(idx, q_terms, q_idf, q_off, p, "hs_bm25_score_docs");
+    if (rc != HS_OK) return rc;
+    const int64_t warps = (int64_t)B * C;
+    const int64_t blocks = (warps * 32 + 255) / 256;
+    bm25_docs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, doc_ids, C, out, B);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Shared device/host helpers for the hs_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/hs_b200.h"
+
+// ---------------------------------------------------------------- index handle (host side)
+struct hs_index {
+    int device = 0;
+    int num_sms = 148;
+    int64_t n_docs = 0;
+    int64_t doc_base = 0;
+    // dense
+    const float* vectors = nullptr;
+    const float* vnorm = nullptr;
+    int32_t dim = 0;
+    int64_t ld = 0;
+    // csr
+    const int64_t* indptr = nullptr;
+    const uint2* postings = nullptr;
+    int64_t n_terms = 0;
+    int64_t n_postings = 0;
+    // doc stats
+    const uint32_t* dl = nullptr;
+    const double* kd_table = nullptr;
+    uint32_t max_dl = 0;
+    double avgdl = 0.0, k1 = 1.5, b = 0.75;
+};
+
+// ---------------------------------------------------------------- error plumbing
+void hs_set_error(const char* fmt, ...);
+
+#define HS_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            hs_set_error(__VA_ARGS__);        \
+            return HS_ERR_ARG;                \
+        }                                     \
+    } while (0)
+
+#define HS_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            hs_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return HS_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+#define HS_LAUNCH_CHECK()                                                               \
+    do {                                                                                \
+        cudaError_t e_ = cudaGetLastError();                                            \
+        if (e_ != cudaSuccess) {                                                        \
+            hs_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return HS_ERR_CUDA;                                                         \
+        }                                                                               \
+    } while (0)
+
+// ---------------------------------------------------------------- order-preserving encodings
+// float -> uint32 such that a < b  <=>  enc(a) < enc(b) (total order, -0 < +0)
+__host__ __device__ __forceinline__ uint32_t hs_enc_f32(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float hs_dec_f32(uint32_t e) {
+    uint32_t u = (e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+// ranking key: larger = better under (score desc, doc_id asc). +0.0 and -0.0 rank equal.
+__device__ __forceinline__ uint64_t hs_make_key(float score, uint32_t doc_id) {
+    if (score == 0.0f) score = 0.0f;  // fold -0.0 into +0.0 so ties fall to doc_id like the host sort
+    return ((uint64_t)hs_enc_f32(score) << 32) | (uint64_t)(0xFFFFFFFFu - doc_id);
+}
+
+// stats slots
+#define HS_STAT_MIN_A 0
+#define HS_STAT_MAX_A 1
+#define HS_STAT_MAX_B 2
+#define HS_STAT_MIN_B 3
+
+// ---------------------------------------------------------------- warp helpers
+__device__ __forceinline__ double hs_shfl_xor_f64(double v, int mask) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xFFFFFFFFu, lo, mask);
+    hi = __shfl_xor_sync(0xFFFFFFFFu, hi, mask);
+    return __hiloint2double(hi, lo);
+}
+// butterfly 16,8,4,2,1 -- every lane ends with the same bits (a+b == b+a in IEEE)
+__device__ __forceinline__ double hs_warp_sum_f64(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = __dadd_rn(v, hs_shfl_xor_f64(v, m));
+    return v;
+}
+__device__ __forceinline__ float hs_warp_sum_f32(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, m));
+    return v;
+}
+
+static inline int hs_num_sms(int device) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n > 0 ? n : 148;
+}

@@ -1,0 +1,296 @@
+"""Batched search over one device shard (and, with a process group, over doc-sharded GPUs).
+
+Data flow of one query batch (B queries), all on the current CUDA stream, nothing synchronises:
+
+    stats_reset
+    K2 dense_scan      -> cos  [B, n] float32   + (min, max) per query      (utils.py:28-54,67-68)
+    K1 bm25_score      -> bm25 [B, n] float32   + max per query             (bm25.py:83-127, pipelines.py:332)
+    [sharded] C2: one all-reduce(MAX) of (-min_cos, max_cos, max_bm, -min_lex) per query
+    K3+K4 fuse_topk    -> per-shard top-k ranking keys [B, k]               (core.py:264-271, pipelines.py:331-343)
+    [sharded] C1: all-gather of the key lists + merge kernel
+    keys_unpack        -> (float32 score, int64 global doc id)
+
+Every rank ends with the same merged result.  Sharded == unsharded bit for bit: min/max are exact
+under any reduction order, per-doc scores depend only on the doc and the global statistics, and the
+merge is a pure comparison on 64-bit keys.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DENSE_MODES, HS_FUSE_HYBRID_BM25, HS_FUSE_RAW, HS_FUSE_SEARCHER, HS_TOPK_MAX, check,
+                   ptr, stream_ptr)
+from .index import DeviceIndex
+
+
+@dataclass
+class QueryBatch:
+    """Host-side description of B queries: vectors [B, dim] float32 and/or term-id lists."""
+    vectors: Optional[np.ndarray] = None                  # float32 [B, dim]
+    term_ids: Optional[Sequence[Sequence[int]]] = None    # per query: known term ids, in order, dups kept
+
+    def __len__(self):
+        if self.vectors is not None:
+            return len(self.vectors)
+        return len(self.term_ids)
+
+
+class SearchEngine:
+    def __init__(self, shard: DeviceIndex, group=None, max_batch: int = 32, dense_mode: str = "exact"):
+        self.shard = shard
+        self.lib = shard.lib
+        self.device = shard.device
+        self.group = group
+        self.world = 1
+        if group is not None:
+            import torch.distributed as dist
+            self.world = dist.get_world_size(group)
+        self.max_batch = int(max_batch)
+        self.dense_mode = dense_mode
+        self._bufs = {}
+        self.launches = 0          # kernels launched by this engine (bench.py: gpu_launches)
+
+    # ------------------------------------------------------------------ buffers (never on the hot path twice)
+    def _buf(self, name: str, shape, dtype) -> torch.Tensor:
+        need = int(np.prod(shape)) if len(shape) else 1
+        t = self._bufs.get(name)
+        if t is None or t.numel() < need or t.dtype != dtype:
+            t = torch.empty(max(need, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t[:need].view(*shape)
+
+    def _pinned(self, name: str, shape, dtype) -> torch.Tensor:
+        need = int(np.prod(shape)) if len(shape) else 1
+        key = "pin_" + name
+        t = self._bufs.get(key)
+        if t is None or t.numel() < need or t.dtype != dtype:
+            t = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
+            self._bufs[key] = t
+        return t[:need].view(*shape)
+
+    # ------------------------------------------------------------------ query upload
+    def upload_vectors(self, q: np.ndarray) -> torch.Tensor:
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.shard.dim:
+            raise ValueError(f"query vectors must be [B, {self.shard.dim}], got {q.shape}")
+        pin = self._pinned("qv", q.shape, torch.float32)
+        pin.copy_(torch.from_numpy(q))
+        dev = self._buf("qv", q.shape, torch.float32)
+        dev.copy_(pin, non_blocking=True)
+        return dev
+
+    def upload_terms(self, term_ids: Sequence[Sequence[int]]):
+        """-> (q_terms int32 [T], q_idf float64 [T], q_off int32 [B+1]) on the device."""
+        idf = self.shard.idf_host
+        df = self.shard.df_host
+        off = [0]
+        flat: List[int] = []
+        for ids in term_ids:
+            # bm25.py:100 -- terms that are in no document have no idf entry and are skipped
+            flat.extend(int(t) for t in ids if 0 <= int(t) < len(df) and df[int(t)] > 0)
+            off.append(len(flat))
+        T = len(flat)
+        pin_t = self._pinned("qt", (max(T, 1),), torch.int32)
+        pin_i = self._pinned("qi", (max(T, 1),), torch.float64)
+        pin_o = self._pinned("qo", (len(off),), torch.int32)
+        if T:
+            arr = np.asarray(flat, dtype=np.int64)
+            pin_t[:T].copy_(torch.from_numpy(arr.astype(np.int32)))
+            pin_i[:T].copy_(torch.from_numpy(idf[arr]))
+        pin_o.copy_(torch.tensor(off, dtype=torch.int32))
+        d_t = self._buf("qt", (max(T, 1),), torch.int32)
+        d_i = self._buf("qi", (max(T, 1),), torch.float64)
+        d_o = self._buf("qo", (len(off),), torch.int32)
+        d_t.copy_(pin_t, non_blocking=True)
+        d_i.copy_(pin_i, non_blocking=True)
+        d_o.copy_(pin_o, non_blocking=True)
+        return d_t, d_i, d_o
+
+    # ------------------------------------------------------------------ kernels
+    def _stats(self, B: int) -> torch.Tensor:
+        s = self._buf("stats", (B, 4), torch.int32)
+        check(self.lib.hs_stats_reset(ptr(s), B, stream_ptr(self.device)), "hs_stats_reset")
+        self.launches += 1
+        return s
+
+    def dense_scan(self, q_dev: torch.Tensor, stats: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
+        B = q_dev.shape[0]
+        cos = self._buf("cos", (B, self.shard.n_docs), torch.float32)
+        m = DENSE_MODES[mode or self.dense_mode]
+        check(self.lib.hs_dense_scan(self.shard.handle, ptr(q_dev), B, q_dev.stride(0), m, ptr(cos), ptr(stats),
+                                     stream_ptr(self.device)), "hs_dense_scan")
+        self.launches += self.dense_launches(B, mode)
+        return cos
+
+    def dense_launches(self, B: int, mode: Optional[str] = None) -> int:
+        nchunk = (self.shard.dim + 127) // 128
+        nchunk = nchunk if nchunk <= 4 else (6 if nchunk <= 6 else 8)
+        budget, cap = (12, 4) if (mode or self.dense_mode) == "exact" else (24, 8)
+        bq = 1
+        while bq * 2 <= budget // nchunk and bq * 2 <= cap:
+            bq *= 2
+        n, b = 0, B
+        while b > 0:
+            step = bq
+            while step > b:
+                step //= 2
+            b -= step
+            n += 1
+        return n
+
+    def bm25_score(self, q_terms, q_idf, q_off, B: int, stats: Optional[torch.Tensor]) -> torch.Tensor:
+        sc = self._buf("bm25", (B, self.shard.n_docs), torch.float32)
+        check(self.lib.hs_bm25_score(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, ptr(sc),
+                                     ptr(stats), stream_ptr(self.device)), "hs_bm25_score")
+        self.launches += 1
+        return sc
+
+    def _exchange_stats(self, stats: torch.Tensor, B: int) -> torch.Tensor:
+        """C2: global (min, max) per query across shards -- one all-reduce(MAX) of B x 4 floats."""
+        if self.group is None or self.world == 1:
+            return stats
+        import torch.distributed as dist
+        f = self._buf("stats_f", (B, 4), torch.float32)
+        st = stream_ptr(self.device)
+        check(self.lib.hs_stats_decode(ptr(stats), ptr(f), B, st), "hs_stats_decode")
+        f[:, 0].neg_()
+        f[:, 3].neg_()
+        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.group)
+        f[:, 0].neg_()
+        f[:, 3].neg_()
+        check(self.lib.hs_stats_encode(ptr(f), ptr(stats), B, st), "hs_stats_encode")
+        self.launches += 2
+        return stats
+
+    def fuse_topk(self, mode: int, a: torch.Tensor, b: Optional[torch.Tensor], stats: Optional[torch.Tensor],
+                  wa: float, wb: float, k: int, below: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """-> ranking keys int64-typed bit patterns [B, k] (merged across shards when sharded)."""
+        B = a.shape[0]
+        n = self.shard.n_docs
+        ws_bytes = self.lib.hs_fuse_topk_workspace_bytes(n, B, k)
+        ws = self._buf("topk_ws", (max(ws_bytes // 8, 1),), torch.int64)
+        keys = self._buf("keys", (B, k), torch.int64)
+        check(self.lib.hs_fuse_topk(self.shard.handle, mode, ptr(a), ptr(b), ptr(stats), float(wa), float(wb),
+                                    B, k, ptr(below), ptr(ws), ws_bytes, ptr(keys), stream_ptr(self.device)),
+              "hs_fuse_topk")
+        self.launches += 2 if n > 0 else 0
+        if self.group is not None and self.world > 1:
+            import torch.distributed as dist
+            gathered = self._buf("keys_all", (self.world, B, k), torch.int64)
+            dist.all_gather_into_tensor(gathered.view(-1), keys.view(-1), group=self.group)   # C1
+            merged = self._buf("keys_merged", (B, k), torch.int64)
+            check(self.lib.hs_topk_merge(ptr(gathered), self.world, B, k, ptr(merged),
+                                         stream_ptr(self.device)), "hs_topk_merge")
+            self.launches += 1
+            keys = merged
+        return keys
+
+    def unpack(self, keys: torch.Tensor):
+        B, k = keys.shape
+        sc = self._buf("out_sc", (B, k), torch.float32)
+        ids = self._buf("out_id", (B, k), torch.int64)
+        check(self.lib.hs_keys_unpack(ptr(keys), B * k, ptr(sc), ptr(ids), stream_ptr(self.device)),
+              "hs_keys_unpack")
+        self.launches += 1
+        return sc, ids
+
+    # ------------------------------------------------------------------ paged select for k > HS_TOPK_MAX
+    def _select(self, mode, a, b, stats, wa, wb, k):
+        k_total = int(k)
+        if k_total <= HS_TOPK_MAX:
+            return self.fuse_topk(mode, a, b, stats, wa, wb, k_total)
+        B = a.shape[0]
+        pages, below, got = [], None, 0
+        while got < k_total:
+            kk = min(HS_TOPK_MAX, k_total - got)
+            keys = self.fuse_topk(mode, a, b, stats, wa, wb, kk, below).clone()
+            pages.append(keys)
+            got += kk
+            if got < k_total:
+                # next page: strictly below the last key of this page (0 = exhausted -> nothing passes)
+                below = keys[:, -1].contiguous().clone()
+        return torch.cat(pages, dim=1)
+
+    # ------------------------------------------------------------------ whole searches (device tensors out)
+    def _batches(self, B: int):
+        for s in range(0, B, self.max_batch):
+            yield s, min(B, s + self.max_batch)
+
+    def search_hybrid_bm25(self, qb: QueryBatch, k: int, ws: float, wl: float, dense_mode: Optional[str] = None):
+        """HybridBM25Pipeline.search (pipelines.py:315-357) for a batch.  -> (scores [B,k], ids [B,k])."""
+        return self._run(qb, k, HS_FUSE_HYBRID_BM25, ws, wl, True, True, dense_mode)
+
+    def search_semantic(self, qb: QueryBatch, k: int, sw: float = 1.0, dense_mode: Optional[str] = None):
+        """Searcher.search with lexical weight 0 (pipelines.py:317-324,474-481): min-max cosine * sw."""
+        return self._run(qb, k, HS_FUSE_SEARCHER, sw, 0.0, True, False, dense_mode)
+
+    def search_searcher(self, qb: QueryBatch, lex: np.ndarray, k: int, sw: float, lw: float,
+                        dense_mode: Optional[str] = None):
+        """Searcher.search with a lexical vector (core.py:261-271): lex float32 [B, n_docs] (host)."""
+        return self._run(qb, k, HS_FUSE_SEARCHER, sw, lw, True, False, dense_mode, lex=lex)
+
+    def search_bm25(self, qb: QueryBatch, k: int):
+        """BM25.search (bm25.py:129-142): raw float32 BM25 score, canonical tie order."""
+        return self._run(qb, k, HS_FUSE_RAW, 1.0, 0.0, False, True, None)
+
+    def _run(self, qb, k, mode, wa, wb, use_dense, use_bm25, dense_mode, lex=None):
+        B = len(qb)
+        out_s, out_i = [], []
+        with torch.cuda.device(self.device):
+            for s, e in self._batches(B):
+                nb = e - s
+                stats = self._stats(nb)
+                cos = bm = None
+                if use_dense:
+                    qd = self.upload_vectors(qb.vectors[s:e])
+                    cos = self.dense_scan(qd, stats, dense_mode)
+                if use_bm25:
+                    qt, qi, qo = self.upload_terms(qb.term_ids[s:e])
+                    bm = self.bm25_score(qt, qi, qo, nb, stats)
+                if lex is not None:
+                    lx = np.ascontiguousarray(lex[s:e], dtype=np.float32)
+                    bm = self._buf("lex", lx.shape, torch.float32)
+                    bm.copy_(torch.from_numpy(lx), non_blocking=False)
+                    check(self.lib.hs_stats_fold_minmax(ptr(bm), self.shard.n_docs, nb, 3, 2, ptr(stats),
+                                                        stream_ptr(self.device)), "hs_stats_fold_minmax")
+                    self.launches += 1
+                if mode != HS_FUSE_RAW:
+                    stats = self._exchange_stats(stats, nb)
+                a, b = (cos, bm) if use_dense else (bm, None)
+                keys = self._select(mode, a, b, stats, wa, wb, k)
+                sc, ids = self.unpack(keys)
+                out_s.append(sc.clone() if e < B or s > 0 else sc)
+                out_i.append(ids.clone() if e < B or s > 0 else ids)
+        if len(out_s) == 1:
+            return out_s[0], out_i[0]
+        return torch.cat(out_s), torch.cat(out_i)
+
+    # ------------------------------------------------------------------ small kernels
+    def bm25_score_docs(self, term_ids: Sequence[Sequence[int]], doc_ids: torch.Tensor) -> torch.Tensor:
+        """BM25.score on candidate docs (pipelines.py:485).  doc_ids int64 [B, C] shard-local."""
+        B, Cn = doc_ids.shape
+        with torch.cuda.device(self.device):
+            qt, qi, qo = self.upload_terms(term_ids)
+            out = self._buf("bm25_docs", (B, Cn), torch.float64)
+            check(self.lib.hs_bm25_score_docs(self.shard.handle, ptr(qt), ptr(qi), ptr(qo), B,
+                                              ptr(doc_ids.contiguous()), Cn, ptr(out), stream_ptr(self.device)),
+                  "hs_bm25_score_docs")
+            self.launches += 1
+        return out
+
+    def mmr(self, cand_ids: torch.Tensor, rel: torch.Tensor, lam: float, k: int) -> torch.Tensor:
+        """DiversityPipeline._mmr (pipelines.py:531-569).  cand_ids int64 [B, C], rel float64 [B, C]."""
+        B, Cn = cand_ids.shape
+        with torch.cuda.device(self.device):
+            nbytes = self.lib.hs_mmr_workspace_bytes(B, Cn)
+            ws = self._buf("mmr_ws", (max((nbytes + 7) // 8, 1),), torch.int64)
+            out = self._buf("mmr_out", (B, k), torch.int32)
+            check(self.lib.hs_mmr(self.shard.handle, ptr(cand_ids.contiguous()), ptr(rel.contiguous()), float(lam),
+                                  B, Cn, k, ptr(ws), nbytes, ptr(out), stream_ptr(self.device)), "hs_mmr")
+            self.launches += 1
+        return out

@@ -1,0 +1,185 @@
+"""Device-resident index shard: the HBM layout behind the C-ABI handle ``hs_index``.
+
+HBM layout of one shard (docs ``doc_base .. doc_base + n_docs - 1``):
+
+    vectors   float32 [n_docs, ld]      row-major, ld = dim rounded up to 4, padding columns zero
+    vnorm     float32 [n_docs]          f32(sqrt(sum64 v^2)) per row, conformance order
+    indptr    int64   [n_terms + 1]     CSR over GLOBAL term ids, restricted to this shard's docs
+    postings  uint32  [n_postings, 2]   (doc_id local to the shard, tf), doc ids ascending per term
+    dl        uint32  [n_docs]          tokens after stop-word removal (bm25.py:59-60)
+    kd_table  float64 [max_dl + 1]      k1 * (1 - b + b * dl / avgdl) per possible doc length
+    idf       float64 [n_terms]         host copy too; ln((N - df + .5) / (df + .5) + 1) (bm25.py:81)
+
+Corpus-global statistics (N, df -> idf, avgdl) are replicated on every shard.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def idf_from_df(doc_count: int, df: np.ndarray) -> np.ndarray:
+    """bm25.py:76-81 on the host with libm ``math.log`` (one call per distinct df value)."""
+    df = np.asarray(df, dtype=np.int64)
+    if df.size == 0:
+        return np.zeros(0, np.float64)
+    uniq, inv = np.unique(df, return_inverse=True)
+    vals = np.fromiter((math.log((doc_count - int(d) + 0.5) / (int(d) + 0.5) + 1) for d in uniq),
+                       dtype=np.float64, count=len(uniq))
+    return vals[inv]
+
+
+class DeviceIndex:
+    """Owns the torch tensors of one shard and the matching ``hs_index`` handle."""
+
+    def __init__(self, device, n_docs: int, doc_base: int = 0):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.HsError("DeviceIndex needs a CUDA device: the hot path has no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n_docs = int(n_docs)
+        self.doc_base = int(doc_base)
+        h = C.c_void_p()
+        check(self.lib.hs_index_create(self.device.index, self.n_docs, self.doc_base, C.byref(h)),
+              "hs_index_create")
+        self.handle = h
+        self.dim = 0
+        self.ld = 0
+        self.vectors = self.vnorm = None
+        self.indptr = self.postings = self.dl = self.kd_table = None
+        self.n_terms = 0
+        self.avgdl = 0.0
+        self.k1, self.b = 1.5, 0.75
+        self.idf_host: Optional[np.ndarray] = None      # float64 [n_terms], global
+        self.df_host: Optional[np.ndarray] = None       # int64 [n_terms], global
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.hs_index_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ dense part
+    def set_dense(self, vectors: torch.Tensor):
+        """``vectors`` float32 [n_docs, dim] on this device (indexer.py:285)."""
+        if vectors.dim() != 2 or vectors.shape[0] != self.n_docs:
+            raise ValueError(f"vectors must be [n_docs={self.n_docs}, dim], got {tuple(vectors.shape)}")
+        vectors = vectors.to(self.device, torch.float32)
+        dim = vectors.shape[1]
+        ld = (dim + 3) // 4 * 4
+        if ld != dim:
+            padded = torch.zeros((self.n_docs, ld), dtype=torch.float32, device=self.device)
+            padded[:, :dim] = vectors
+            vectors = padded
+        self.vectors = vectors.contiguous()
+        self.dim, self.ld = dim, ld
+        self.vnorm = torch.empty(self.n_docs, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.hs_row_norms(ptr(self.vectors), self.n_docs, dim, ld, ptr(self.vnorm),
+                                        stream_ptr(self.device)), "hs_row_norms")
+            check(self.lib.hs_index_set_dense(self.handle, ptr(self.vectors), dim, ld, ptr(self.vnorm)),
+                  "hs_index_set_dense")
+
+    # ------------------------------------------------------------------ lexical part
+    def set_bm25(self, indptr: torch.Tensor, postings: torch.Tensor, dl: torch.Tensor, avgdl: float,
+                 df_global: np.ndarray, n_docs_global: int, k1: float = 1.5, b: float = 0.75,
+                 max_dl: Optional[int] = None):
+        """CSR + doc stats.  ``postings`` int32 [P, 2] holding (local doc id, tf) bit patterns."""
+        self.indptr = indptr.to(self.device, torch.int64).contiguous()
+        self.postings = postings.to(self.device, torch.int32).contiguous().view(-1, 2)
+        self.dl = dl.to(self.device, torch.int32).contiguous()
+        self.n_terms = self.indptr.numel() - 1
+        self.avgdl, self.k1, self.b = avgdl, float(k1), float(b)
+        self.df_host = np.asarray(df_global, dtype=np.int64)
+        self.idf_host = idf_from_df(n_docs_global, self.df_host)
+        if max_dl is None:
+            max_dl = int(self.dl.max().item()) if self.n_docs else 0
+        self.max_dl = int(max_dl)
+        with torch.cuda.device(self.device):
+            st = stream_ptr(self.device)
+            self.kd_table = None
+            if avgdl > 0 and self.max_dl <= (1 << 22):
+                self.kd_table = torch.empty(self.max_dl + 1, dtype=torch.float64, device=self.device)
+                check(self.lib.hs_bm25_kd_table(float(avgdl), self.k1, self.b, self.max_dl,
+                                                ptr(self.kd_table), st), "hs_bm25_kd_table")
+            check(self.lib.hs_index_set_csr(self.handle, ptr(self.indptr), ptr(self.postings), self.n_terms,
+                                            self.postings.shape[0]), "hs_index_set_csr")
+            check(self.lib.hs_index_set_doc_stats(self.handle, ptr(self.dl), float(avgdl), self.k1, self.b,
+                                                  ptr(self.kd_table), self.max_dl), "hs_index_set_doc_stats")
+
+    @property
+    def has_dense(self) -> bool:
+        return self.vectors is not None
+
+    @property
+    def has_bm25(self) -> bool:
+        return self.indptr is not None
+
+
+# ---------------------------------------------------------------------- host-side lexical statistics
+class LexicalStats:
+    """Host mirror of ``BM25.fit`` (bm25.py:45-81): vocabulary, per-doc term ids, df, dl, avgdl.
+
+    Defines *term identity* (tokeniser + stop words) for the device CSR; the arithmetic itself runs in
+    the CUDA kernels.
+    """
+
+    def __init__(self, remove_stopwords: bool = True):
+        self.remove_stopwords = remove_stopwords
+        self.vocab: Dict[str, int] = {}
+        self.doc_count = 0
+        self.doc_lengths = np.zeros(0, np.int64)
+        self.avg_doc_len = 0
+        self.indptr = np.zeros(1, np.int64)
+        self.postings = np.zeros((0, 2), np.uint32)
+        self.df = np.zeros(0, np.int64)
+
+    def fit(self, documents: Sequence[str]):
+        from .extractor import extract_tokens
+        vocab: Dict[str, int] = {}
+        lens: List[int] = []
+        flat: List[int] = []
+        for doc in documents:
+            toks = extract_tokens(doc, remove_stopwords=self.remove_stopwords)
+            lens.append(len(toks))
+            flat.extend(vocab.setdefault(t, len(vocab)) for t in toks)
+        n = len(documents)
+        self.vocab = vocab
+        self.doc_count = n
+        self.doc_lengths = np.asarray(lens, dtype=np.int64)
+        # bm25.py:71 -- python int sum / count (0 when the corpus is empty)
+        self.avg_doc_len = (int(self.doc_lengths.sum()) / n) if n > 0 else 0
+        v = len(vocab)
+        if flat:
+            terms = np.asarray(flat, dtype=np.int64)
+            docs = np.repeat(np.arange(n, dtype=np.int64), self.doc_lengths)
+            uk, tf = np.unique(terms * max(n, 1) + docs, return_counts=True)   # sorted by (term, doc)
+            pt, pd = uk // max(n, 1), uk % max(n, 1)
+        else:
+            pt = pd = tf = np.zeros(0, np.int64)
+        self.df = np.bincount(pt, minlength=v).astype(np.int64)
+        self.indptr = np.concatenate([[0], np.cumsum(self.df)]).astype(np.int64)
+        self.postings = np.stack([pd.astype(np.uint32), tf.astype(np.uint32)], axis=1) if len(pd) else \
+            np.zeros((0, 2), np.uint32)
+        return self
+
+    def query_term_ids(self, query: str) -> List[int]:
+        """bm25.py:94,99-101 -- query tokens in order, duplicates kept, unknown terms dropped."""
+        from .extractor import extract_tokens
+        out = []
+        for t in extract_tokens(query, remove_stopwords=self.remove_stopwords):
+            tid = self.vocab.get(t)
+            if tid is not None:
+                out.append(tid)
+        return out

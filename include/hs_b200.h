@@ -1,0 +1,147 @@
+/*
+ * hs_b200.h -- C ABI of the B200-native hybrid scoring path.
+ *
+ * Drop-in boundary for the hot path behind the reference's
+ *   create_pipeline("basic"|"bm25"|"hybrid_bm25"|"multi_stage"|"diversity").index()/search()
+ * (reference: search_engine/pipelines.py:617-646).  The reference is pure Python and has no FFI of
+ * its own; each entry point below names the reference compute site (file:line, all under
+ * /root/reference/search_engine/) it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative hs_status otherwise; hs_last_error() gives the
+ *     message for the calling thread
+ *   - pointers are DEVICE pointers owned by the caller unless the name ends in _host
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream ordered, nothing synchronises
+ *   - no allocation on the hot path: scratch comes in through `workspace` arguments whose sizes the
+ *     *_workspace_bytes() functions report
+ *   - doc ids are uint32 positions in the shard plus the shard's doc_base (global id < 2^32)
+ *   - ranking order is the total order (score desc, doc_id asc); it is carried in a 64-bit key
+ *       key = ordered_u32(score) << 32 | (0xFFFFFFFF - doc_id)          larger key = better rank
+ */
+#ifndef HS_B200_H
+#define HS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_ABI_VERSION 1
+
+typedef enum {
+    HS_OK = 0,
+    HS_ERR_ARG = -1,       /* bad argument (null pointer, size, alignment, unsupported shape) */
+    HS_ERR_CUDA = -2,      /* a CUDA runtime call failed; message holds cudaGetErrorString */
+    HS_ERR_STATE = -3      /* index is missing the part this call needs (dense / csr / stats) */
+} hs_status;
+
+/* dense arithmetic modes (utils.py:28-54 batch_cosine_sim) */
+typedef enum {
+    HS_DENSE_EXACT = 0,    /* float64 accumulation in the conformance order: bit-identical to oracle */
+    HS_DENSE_FP32 = 1,     /* float32 FMA accumulation, same lane order (as precise as the reference) */
+    HS_DENSE_BF16 = 2      /* bf16 tcgen05 GEMM at large query batch (stage-1 retrieval, 1e-2) */
+} hs_dense_mode;
+
+/* score fusion formulas */
+typedef enum {
+    HS_FUSE_RAW = 0,          /* key = a[i]                      bm25.py:141 / utils.py:74-87            */
+    HS_FUSE_SEARCHER = 1,     /* f32(norm(a)*f32(w_a)) + f32(norm(b)*f32(w_b))    core.py:264-268        */
+    HS_FUSE_HYBRID_BM25 = 2   /* f32(f64(norm(a))*w_a) + f32(b/max_b)*f32(w_b)    pipelines.py:331-340   */
+} hs_fuse_mode;
+
+typedef struct hs_index hs_index;
+
+int         hs_abi_version(void);
+const char* hs_last_error(void);
+
+/* ---- index handle: one per GPU shard (replaces the pipeline object's numpy/dict state,
+ *      pipelines.py:302-313, bm25.py:45-81) ------------------------------------------------------- */
+int hs_index_create(int device, int64_t n_docs, int64_t doc_base, hs_index** out);
+int hs_index_destroy(hs_index* idx);
+/* float32 rows [n_docs, ld] (ld % 4 == 0, base 16-byte aligned, columns >= dim are zero) and their
+ * float32 L2 norms from hs_row_norms (indexer.py:285 `vectors`; norms: utils.py:47) */
+int hs_index_set_dense(hs_index* idx, const float* vectors, int32_t dim, int64_t ld, const float* vnorm);
+/* inverted index over term ids: indptr int64[n_terms+1], postings (doc_id u32, tf u32)[n_postings],
+ * doc ids local to the shard and ascending inside each list (bm25.py:62-67 term_freqs, transposed) */
+int hs_index_set_csr(hs_index* idx, const int64_t* indptr, const uint32_t* postings, int64_t n_terms,
+                     int64_t n_postings);
+/* doc lengths u32[n_docs] after stop-word removal (bm25.py:59-60), corpus-global avgdl (bm25.py:71),
+ * k1, b (bm25.py:19-33); kd_table double[max_dl+1] from hs_bm25_kd_table or NULL to compute inline */
+int hs_index_set_doc_stats(hs_index* idx, const uint32_t* dl, double avgdl, double k1, double b,
+                           const double* kd_table, uint32_t max_dl);
+
+/* ---- index-time kernels ------------------------------------------------------------------------ */
+/* vnorm[i] = f32(sqrt(sum64 v[i,:]^2)), conformance order (utils.py:47 np.linalg.norm per row) */
+int hs_row_norms(const float* vectors, int64_t n, int32_t dim, int64_t ld, float* vnorm, void* stream);
+/* kd[l] = k1 * ((1 - b) + b * (l / avgdl)) in float64, reference operation order (bm25.py:108) */
+int hs_bm25_kd_table(double avgdl, double k1, double b, uint32_t max_dl, double* kd, void* stream);
+
+/* ---- hot path ---------------------------------------------------------------------------------- */
+/* stats: uint32[B][4] order-preserving encodings {min_a, max_a, max_b, min_b}; reset before a batch */
+int hs_stats_reset(uint32_t* stats_enc, int32_t B, void* stream);
+int hs_stats_decode(const uint32_t* stats_enc, float* stats, int32_t B, void* stream);
+int hs_stats_encode(const float* stats, uint32_t* stats_enc, int32_t B, void* stream);
+/* fold min/max of x float32 [B, n] into stats slots (utils.py:67-68 for an externally produced vector,
+ * e.g. the lexical scores of core.py:261); slot < 0 skips that bound */
+int hs_stats_fold_minmax(const float* x, int64_t n, int32_t B, int32_t slot_min, int32_t slot_max,
+                         uint32_t* stats_enc, void* stream);
+
+/* K2  batch_cosine_sim (utils.py:28-54) for B queries [B, ld_q] against every row of the shard:
+ *     cos[b, i] float32 [B, n_docs]; folds min/max into stats slots 0/1 (utils.py:67-68) */
+int hs_dense_scan(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
+                  float* cos, uint32_t* stats_enc, void* stream);
+
+/* K1  BM25.score_batch (bm25.py:83-127) for B queries over the CSR: query b owns tokens
+ *     q_off[b]..q_off[b+1]-1 (known terms only, query order, duplicates kept) with their float64 idf
+ *     (bm25.py:81).  scores float32 [B, n_docs] (single rounding of the float64 sum, bm25.py:124-126);
+ *     folds max into stats slot 2 (pipelines.py:332).  plus_delta < 0: Okapi; >= 0: BM25Plus is not
+ *     sparse and is rejected here (see hs_bm25plus_... in a later ABI version). */
+int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                  int32_t B, float* scores, uint32_t* stats_enc, void* stream);
+
+/* BM25.score (bm25.py:83-112) for selected docs only: multi_stage stage 2 (pipelines.py:485).
+ * doc_ids int64 [B, C] (shard-local, < 0 = padding), out float64 [B, C], unrounded */
+int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf,
+                       const int32_t* q_off, int32_t B, const int64_t* doc_ids, int32_t C, double* out,
+                       void* stream);
+
+/* K3+K4  normalize_scores + weighted fusion (utils.py:57-71, core.py:264-268, pipelines.py:331-340)
+ *     fused into the top-k select (core.py:271, bm25.py:141, pipelines.py:342-343): per-CTA partial
+ *     top-k lists into `workspace`, then one merge.  a, b: float32 [B, n_docs] (b may be NULL when
+ *     w_b == 0).  Only keys < below_key[b] take part (pass NULL for no bound): lets a caller page
+ *     past k = HS_TOPK_MAX.  out_keys uint64 [B, k], descending, 0 = no entry. */
+#define HS_TOPK_MAX 2048
+size_t hs_fuse_topk_workspace_bytes(int64_t n_docs, int32_t B, int32_t k);
+int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const float* b,
+                 const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
+                 const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                 void* stream);
+/* C1 merge: keys uint64 [n_lists, B, k] (e.g. the all-gathered per-shard lists) -> out_keys [B, k] */
+int hs_topk_merge(const uint64_t* keys, int32_t n_lists, int32_t B, int32_t k, uint64_t* out_keys,
+                  void* stream);
+/* keys -> (float32 score, int64 global doc id; -1 where key == 0) */
+int hs_keys_unpack(const uint64_t* keys, int64_t count, float* scores, int64_t* doc_ids, void* stream);
+
+/* K5  DiversityPipeline._mmr (pipelines.py:531-569): greedy MMR over C candidates per query.
+ *     cand_ids int64 [B, C] shard-local rows of the dense matrix (< 0 = padding), rel float64 [B, C]
+ *     (pipelines.py:589), out_sel int32 [B, k] positions into the candidate list (-1 = none). */
+size_t hs_mmr_workspace_bytes(int32_t B, int32_t C);
+int hs_mmr(const hs_index* idx, const int64_t* cand_ids, const double* rel, double lambda, int32_t B,
+           int32_t C, int32_t k, void* workspace, size_t workspace_bytes, int32_t* out_sel, void* stream);
+
+/* ---- synthetic corpus generators (counter-based; hybrid_search_engine_b200/synth.py is the spec) */
+int hs_synth_embeddings(float* out, int64_t row0, int64_t n, int32_t dim, int64_t ld, uint64_t seed_key,
+                        void* stream);
+int hs_synth_doc_lengths(uint32_t* dl, int64_t doc0, int64_t n, uint64_t seed_key, uint32_t min_len,
+                         uint32_t span, void* stream);
+/* keys[tok_off[i - doc0] + j] = term(i, j) << 32 | (i - doc0)   for doc i in [doc0, doc0 + n) */
+int hs_synth_token_keys(uint64_t* keys, const int64_t* tok_off, const uint32_t* dl, int64_t doc0, int64_t n,
+                        uint64_t seed_key, const uint64_t* thresholds, int32_t vocab, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_B200_H */

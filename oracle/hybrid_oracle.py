@@ -32,7 +32,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 # --------------------------------------------------------------------------- tokeniser
-# extractor.py:6-12 (52 words)
+# extractor.py:6-12 (48 words)
 STOPWORDS = frozenset(
     "a an the and or but in on at to for of with by from is are was were be been being have has "
     "had do does did will would could should may might must shall can this that these those i "

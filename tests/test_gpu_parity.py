@@ -1,0 +1,296 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): CUDA path through the C ABI vs the oracle
+(bit-exact in the conformance modes) and vs the frozen outputs of the unmodified reference.
+
+Tolerances (north star): top-k doc ids bit-exact under (score desc, doc_id asc); BM25 and fused
+scores within 1e-5 relative of the reference in fp32.  Against the oracle the ``exact`` dense mode and
+everything integer / float64-ordered is required to be BIT-IDENTICAL.
+"""
+import numpy as np
+import pytest
+
+from oracle import hybrid_oracle as orc
+from tests.golden_cases import ALL_CASES, load_case
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    import hybrid_search_engine_b200 as hs
+    from hybrid_search_engine_b200 import _lib
+    _lib.load()
+    return hs
+
+
+class TableEncoder:
+    """text -> vector table, the same stand-in the golden generator used for MiniLM."""
+
+    def __init__(self, table, dim):
+        self.table, self.dim = table, dim
+
+    def encode(self, texts, **kw):
+        return np.stack([self.table[t] for t in texts]).astype(np.float32) if len(texts) else \
+            np.zeros((0, self.dim), np.float32)
+
+
+@pytest.fixture(scope="module", params=ALL_CASES)
+def case(request):
+    c = load_case(request.param)
+    c.ix = orc.build_index(c.docs, c.emb)
+    table = {orc.preprocess_text(d): e for d, e in zip(c.docs, c.emb)}
+    table.update({q: e for q, e in zip(c.queries, c.q_emb)})
+    c.encoder = TableEncoder(table, c.emb.shape[1])
+    return c
+
+
+def _near_tie_equal(ids_a, ids_b, score_of, tol):
+    if np.array_equal(ids_a, ids_b):
+        return True
+    return all(a == b or abs(float(score_of[a]) - float(score_of[b])) <= tol for a, b in zip(ids_a, ids_b))
+
+
+# ------------------------------------------------------------------------------------------ kernels
+@pytest.mark.parametrize("n,d", [(1, 4), (7, 48), (300, 100), (1000, 384), (513, 768), (257, 1024), (64, 130)])
+def test_dense_exact_bit_identical_to_oracle(hs, n, d):
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    rng = np.random.default_rng(n * 1000 + d)
+    v = rng.standard_normal((n, d)).astype(np.float32)
+    if n > 5:
+        v[3] = 0.0
+    q = rng.standard_normal((5, d)).astype(np.float32)
+    q[2] = 0.0
+    shard = hs.DeviceIndex("cuda:0", n)
+    shard.set_dense(torch.from_numpy(v).cuda())
+    assert np.array_equal(shard.vnorm.cpu().numpy(), orc.row_norms(v))
+    eng = SearchEngine(shard)
+    for mode in ("exact", "fp32"):
+        stats = eng._stats(5)
+        cos = eng.dense_scan(eng.upload_vectors(q), stats, mode).cpu().numpy()
+        st = stats.cpu().numpy().view(np.uint32)
+        for b in range(5):
+            want = orc.cosine_exact(q[b], v)
+            if mode == "exact":
+                assert np.array_equal(cos[b], want), (mode, b)
+            else:
+                assert np.max(np.abs(cos[b] - want)) <= 2.4e-7
+            from_enc = lambda e: np.array([((~e) & 0xFFFFFFFF) if not (e & 0x80000000) else (e & 0x7FFFFFFF)],
+                                          np.uint32).view(np.float32)[0]
+            assert from_enc(int(st[b, 0])) == cos[b].min()
+            assert from_enc(int(st[b, 1])) == cos[b].max()
+
+
+def test_bm25_scores_bit_identical_to_oracle_and_reference(hs, case):
+    bm = hs.BM25()
+    bm.fit(case.docs)
+    got = bm.score_batch_many(case.queries)
+    for qi, q in enumerate(case.queries):
+        assert np.array_equal(got[qi], orc.bm25_score_batch(case.ix.bm25, q)), q
+        assert np.array_equal(got[qi], case.ref[f"q{qi}_bm25"]), q      # unmodified reference
+    # BM25.score: float64, unrounded (bm25.py:83-112)
+    for qi in (0, 1):
+        tids = orc.query_term_ids(case.ix.bm25, case.queries[qi])
+        want = orc.bm25_score_docs(case.ix.bm25, tids, [0, 5, len(case.docs) - 1])
+        for j, d in enumerate([0, 5, len(case.docs) - 1]):
+            assert bm.score(case.queries[qi], d) == want[j]
+    # idf / statistics in the reference's shapes
+    assert bm.doc_lengths == case.ref["doc_lengths"].tolist()
+    assert float(bm.avg_doc_len) == float(case.ref["avg_doc_len"])
+    idf = bm.idf
+    assert np.array_equal(np.array([idf[t] for t in case.meta["idf_terms"]]), case.ref["idf_vals"])
+
+
+def test_bm25_pipeline(hs, case):
+    p = hs.create_pipeline("bm25")
+    p.index(case.docs)
+    res = p.search_many(case.queries, top_k=10)
+    for qi, q in enumerate(case.queries):
+        ids, sc = orc.search_bm25(case.ix, q, 10)
+        r = res[qi]
+        assert [x["doc_id"] for x in r.results] == ids.tolist()
+        assert [x["score"] for x in r.results] == [float(s) for s in sc]
+        assert all(type(x["score"]) is float and x["content"] == case.docs[x["doc_id"]] for x in r.results)
+        assert r.metadata == {"pipeline": "bm25", "k1": 1.5, "b": 0.75}
+        # reference: scores identical; ids up to its unstable argsort among exact ties
+        assert np.array_equal(np.array([x["score"] for x in r.results]), case.ref[f"q{qi}_bm25_scores"])
+        assert _near_tie_equal(ids, case.ref[f"q{qi}_bm25_ids"], case.ref[f"q{qi}_bm25"], 0.0)
+
+
+def test_hybrid_bm25_pipeline(hs, case):
+    n = len(case.docs)
+    p = hs.create_pipeline("hybrid_bm25", encoder=case.encoder)
+    p.index(case.docs)
+    for k in (5, 100, n):
+        res = p.search_many(case.queries, top_k=k)
+        for qi, q in enumerate(case.queries):
+            ids, sc, fused = orc.search_hybrid_bm25(case.ix, q, case.q_emb[qi], k)
+            r = res[qi]
+            got_ids = np.array([x["doc_id"] for x in r.results])
+            got_sc = np.array([x["score"] for x in r.results], np.float32)
+            assert np.array_equal(got_ids, ids), (k, q)                 # bit-exact vs oracle
+            assert np.array_equal(got_sc, sc), (k, q)
+            assert all(type(x["score"]) is np.float32 for x in r.results)
+            assert all(x["content"] == case.docs[x["doc_id"]] for x in r.results)
+            # vs the unmodified reference: 1e-5 relative, ids up to near-tie groups
+            ref_ids, ref_sc = case.ref[f"q{qi}_hyb_ids"][:k], case.ref[f"q{qi}_hyb_scores"][:k]
+            ref_full = np.empty(n, np.float32)
+            ref_full[case.ref[f"q{qi}_hyb_ids"]] = case.ref[f"q{qi}_hyb_scores"]
+            np.testing.assert_allclose(got_sc, ref_full[got_ids], rtol=1e-5, atol=1e-6)
+            assert _near_tie_equal(got_ids[:100], ref_ids[:100], ref_full, 1e-6)
+    assert res[0].metadata == {"pipeline": "hybrid_bm25", "semantic_weight": 0.6, "bm25_weight": 0.4}
+    one = p.search(case.queries[0], top_k=5)
+    assert [x["doc_id"] for x in one.results] == [x["doc_id"] for x in p.search_many(case.queries[:1], 5)[0].results]
+
+
+def test_hybrid_fp32_mode_within_tolerance(hs, case):
+    p = hs.create_pipeline("hybrid_bm25", encoder=case.encoder, dense_mode="fp32")
+    p.index(case.docs)
+    n = len(case.docs)
+    res = p.search_many(case.queries, top_k=min(100, n))
+    for qi, q in enumerate(case.queries):
+        ids, sc, fused = orc.search_hybrid_bm25(case.ix, q, case.q_emb[qi], min(100, n))
+        got_ids = np.array([x["doc_id"] for x in res[qi].results])
+        got_sc = np.array([x["score"] for x in res[qi].results], np.float32)
+        np.testing.assert_allclose(got_sc, fused[got_ids], rtol=1e-5, atol=1e-6)
+        assert _near_tie_equal(got_ids, ids, fused, 1e-6)
+
+
+def test_multi_stage_pipeline(hs, case):
+    n = len(case.docs)
+    rr = type("RR", (), {"rerank": staticmethod(lambda q, res, top_k=None: res[:top_k] if top_k else res)})()
+    p = hs.create_pipeline("multi_stage", stage1_k=min(100, n), stage2_k=20, encoder=case.encoder, reranker=rr)
+    p.index(case.docs)
+    for qi, q in enumerate(case.queries):
+        s1, s2, s2sc = orc.search_multi_stage(case.ix, q, case.q_emb[qi], min(100, n), 20)
+        r = p.search(q, top_k=20)
+        assert [x["doc_id"] for x in r.results] == s2.tolist()
+        assert [x["score"] for x in r.results] == s2sc.tolist()              # float64, unrounded
+        assert all(x["stage"] == "final" for x in r.results)
+        assert r.metadata == {"pipeline": "multi_stage", "stage1_k": min(100, n), "stage2_k": 20, "final_k": 20}
+        # reference: stage-2 scores for ITS stage-1 candidates are bit-exact when recomputed on the device
+        ref_s1 = case.ref[f"q{qi}_ms_stage1_ids"]
+        ids_t = torch.as_tensor(ref_s1, dtype=torch.int64, device="cuda")[None, :]
+        got = p.searcher.engine.bm25_score_docs([p.bm25.stats.query_term_ids(q)], ids_t).cpu().numpy()[0]
+        assert np.array_equal(got, case.ref[f"q{qi}_ms_stage2_bm25"])
+    assert p.search(case.queries[0]).metadata["final_k"] == 5                 # top_k=None -> final_k
+
+
+def test_mmr_kernel_matches_reference_and_oracle(hs):
+    c = load_case("t1_small")
+    emb = c.emb[:60].copy()
+    emb[31] = emb[30]
+    rel = orc.diversity_relevance(np.linspace(1.0, 0.2, 60).tolist())
+    p = hs.create_pipeline("diversity", lambda_param=0.5)
+    p.index([f"d{i}" for i in range(60)], embeddings=emb)
+    sel = p._mmr(None, np.arange(60), rel, 15)
+    assert sel == c.ref["mmr_sel"].tolist()                                   # unmodified reference
+    assert sel == orc.mmr_select(emb, rel, 0.5, 15)
+    # bigger random case vs oracle, with padding candidates and k == C
+    rng = np.random.default_rng(3)
+    emb = rng.standard_normal((500, 384)).astype(np.float32)
+    emb[7] = 0.0
+    p.index([f"d{i}" for i in range(500)], embeddings=emb)
+    cand = rng.permutation(500)[:200]
+    rel = rng.random(200)
+    assert p._mmr(None, cand, rel, 50) == orc.mmr_select(emb[cand], rel, 0.5, 50)
+    assert p._mmr(None, cand[:10], rel[:10], 10) == orc.mmr_select(emb[cand[:10]], rel[:10], 0.5, 10)
+
+
+# ------------------------------------------------------------------------------------------ select
+@pytest.mark.parametrize("n,k", [(10, 3), (1000, 100), (5000, 128), (100000, 100), (100000, 1000),
+                                 (50000, 2048), (30000, 5000), (300, 300)])
+def test_topk_select_with_ties(hs, n, k):
+    from hybrid_search_engine_b200.engine import SearchEngine
+    from hybrid_search_engine_b200._lib import HS_FUSE_RAW
+    rng = np.random.default_rng(n + k)
+    B = 3
+    x = rng.standard_normal((B, n)).astype(np.float32)
+    x[1] = np.round(x[1], 1)                   # heavy exact ties
+    x[2] = np.sort(x[2])                       # adversarial ascending order
+    x[0, :5] = [0.0, -0.0, 0.0, -0.0, 0.0]
+    shard = hs.DeviceIndex("cuda:0", n)
+    eng = SearchEngine(shard)
+    keys = eng._select(HS_FUSE_RAW, torch.from_numpy(x).cuda(), None, None, 1.0, 0.0, k)
+    sc, ids = eng.unpack(keys)
+    sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
+    for b in range(B):
+        want = orc.canonical_topk(x[b], k)
+        assert np.array_equal(ids[b], want), b
+        assert np.array_equal(sc[b], x[b][want])
+
+
+def test_synth_device_generators_match_numpy(hs):
+    from hybrid_search_engine_b200 import synth, synth_device
+    spec = synth.SynthSpec(n_docs=3000, vocab=5000, dim=100, min_len=5, max_len=40)
+    emb = synth_device.synth_embeddings(spec, 100, 400, "cuda:0").cpu().numpy()
+    assert np.array_equal(emb[:, :100], synth.embeddings(spec, 100, 400))
+    dl = synth_device.synth_doc_lengths(spec, 100, 400, "cuda:0")
+    assert np.array_equal(dl.cpu().numpy().view(np.uint32), synth.doc_lengths(spec, 100, 400))
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, "cuda:0", block_docs=700)
+    # same corpus through the host tokeniser + oracle
+    docs = synth.doc_texts(spec, 0, spec.n_docs)
+    st = orc.bm25_fit(docs)
+    perm = np.array([st.vocab.get(f"t{t}", -1) for t in range(spec.vocab)])
+    indptr = shard.indptr.cpu().numpy()
+    post = shard.postings.cpu().numpy().view(np.uint32)
+    for t in (0, 1, 17, 400, 4999):
+        lo, hi = indptr[t], indptr[t + 1]
+        if perm[t] < 0:
+            assert lo == hi
+            continue
+        olo, ohi = st.indptr[perm[t]], st.indptr[perm[t] + 1]
+        assert np.array_equal(post[lo:hi, 0], st.post_doc[olo:ohi])
+        assert np.array_equal(post[lo:hi, 1], st.post_tf[olo:ohi])
+    assert shard.avgdl == st.avg_doc_len
+
+
+def test_synthetic_shard_search_matches_oracle(hs):
+    """End-to-end on a device-built corpus: hybrid_bm25 ids/scores bit-exact vs the oracle run on the
+    same corpus materialised as text."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=20000, vocab=3000, dim=384, min_len=20, max_len=60)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, "cuda:0")
+    eng = SearchEngine(shard, max_batch=4)
+    docs = synth.doc_texts(spec, 0, spec.n_docs)
+    ix = orc.build_index(docs, synth.embeddings(spec, 0, spec.n_docs))
+    nq = 6
+    qv = synth.query_embeddings(spec, 0, nq)
+    qt = synth.query_terms(spec, 0, nq)
+    sc, ids = eng.search_hybrid_bm25(QueryBatch(vectors=qv, term_ids=qt.tolist()), 100, 0.6, 0.4)
+    sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
+    for qi, q in enumerate(synth.query_texts(spec, 0, nq)):
+        oid, osc, _ = orc.search_hybrid_bm25(ix, q, qv[qi], 100)
+        assert np.array_equal(ids[qi], oid)
+        assert np.array_equal(sc[qi], osc)
+
+
+# ------------------------------------------------------------------------------------------ API behaviour
+def test_errors_and_edge_cases(hs):
+    with pytest.raises(ValueError, match="Unknown pipeline"):
+        hs.create_pipeline("nope")
+    enc = TableEncoder({"a b": np.ones(8, np.float32), "c": np.arange(8, dtype=np.float32), "q": np.ones(8, np.float32)}, 8)
+    # search before index: Searcher-backed pipelines raise AttributeError, bm25 returns []
+    with pytest.raises(AttributeError):
+        hs.create_pipeline("hybrid_bm25", encoder=enc).search("q")
+    assert hs.create_pipeline("bm25").search("q").results == []
+    # empty corpus
+    p = hs.create_pipeline("bm25"); p.index([])
+    assert p.search("q").results == []
+    p = hs.create_pipeline("hybrid_bm25", encoder=enc); p.index([])
+    with pytest.raises(ValueError, match="zero-size array"):
+        p.search("q")
+    # top_k > N returns N; unknown terms -> zero BM25, max falls back to 1
+    p = hs.create_pipeline("hybrid_bm25", encoder=enc); p.index(["a b", "c"])
+    r = p.search("q", top_k=10)
+    assert len(r.results) == 2
+    # weights must sum to one on the Searcher path (core.py:232-233)
+    s = hs.Searcher(encoder=enc)
+    from hybrid_search_engine_b200.core import DocTable
+    with pytest.raises(ValueError, match="must sum to 1.0"):
+        s.search("q", DocTable(["a b", "c"]), np.ones((2, 8), np.float32), semantic_weight=0.7, lexical_weight=0.2)
+    # all-empty docs: all scores 0.0, no error
+    p = hs.create_pipeline("bm25"); p.index(["", "the"])
+    r = p.search("the fox", top_k=5)
+    assert [x["score"] for x in r.results] == [0.0, 0.0] and [x["doc_id"] for x in r.results] == [0, 1]

@@ -1,0 +1,112 @@
+"""CPU-only checks: the C-ABI library loads and exports what include/hs_b200.h declares, the host-side
+logic (tokeniser, lexical statistics, synthetic generators) matches the oracle, and the product path
+fails loudly -- never falls back -- without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import hybrid_oracle as orc
+from tests.golden_cases import load_case
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from hybrid_search_engine_b200 import _lib, build_native
+    build_native.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "hs_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hs_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hs_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import hybrid_search_engine_b200 as hs
+    from hybrid_search_engine_b200._lib import HsError
+    p = hs.create_pipeline("bm25")
+    with pytest.raises(HsError):
+        p.index(["alpha beta", "gamma"])
+    p = hs.create_pipeline("hybrid_bm25")
+    with pytest.raises(HsError):
+        p.index(["alpha beta", "gamma"], embeddings=np.ones((2, 8), np.float32))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hybrid_search_engine_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("bit-identical to oracle", "").replace("to the oracle", ""), fn
+
+
+def test_create_pipeline_names_and_errors():
+    import hybrid_search_engine_b200 as hs
+    with pytest.raises(ValueError, match=r"Unknown pipeline: nope\. Choose from \['basic', 'chunked', 'reranked', "
+                                         r"'bm25', 'hybrid_bm25', 'rag', 'multi_stage', 'diversity'\]"):
+        hs.create_pipeline("nope")
+    for name, cls in (("basic", "BasicPipeline"), ("bm25", "BM25Pipeline"), ("hybrid_bm25", "HybridBM25Pipeline"),
+                      ("multi_stage", "MultiStagePipeline"), ("diversity", "DiversityPipeline")):
+        assert type(hs.create_pipeline(name)).__name__ == cls
+    assert hs.create_pipeline().semantic_weight == 0.7          # default "basic", sw = 0.7
+    p = hs.create_pipeline("multi_stage")
+    assert (p.stage1_k, p.stage2_k, p.final_k) == (100, 20, 5)
+    assert hs.create_pipeline("diversity").lambda_param == 0.5
+    h = hs.create_pipeline("hybrid_bm25", semantic_weight=0.9, bm25_weight=0.9)   # not validated (reference)
+    assert (h.semantic_weight, h.bm25_weight) == (0.9, 0.9)
+    with pytest.raises(NotImplementedError):
+        hs.create_pipeline("rag")
+
+
+@pytest.mark.parametrize("name", ["t0_sample_docs", "t1_small"])
+def test_lexical_stats_match_oracle_fit(name):
+    from hybrid_search_engine_b200.index import LexicalStats, idf_from_df
+    c = load_case(name)
+    st = LexicalStats().fit(c.docs)
+    o = orc.bm25_fit(c.docs)
+    assert st.vocab == o.vocab
+    assert np.array_equal(st.doc_lengths, c.ref["doc_lengths"])
+    assert float(st.avg_doc_len) == float(c.ref["avg_doc_len"])
+    assert np.array_equal(st.indptr, o.indptr)
+    assert np.array_equal(st.postings[:, 0], o.post_doc) and np.array_equal(st.postings[:, 1], o.post_tf)
+    idf = idf_from_df(st.doc_count, st.df)
+    terms = c.meta["idf_terms"]
+    assert np.array_equal(np.array([idf[st.vocab[t]] for t in terms]), c.ref["idf_vals"])   # reference idf
+    for q in c.queries:
+        assert st.query_term_ids(q) == [o.vocab[t] for t in orc.extract_tokens(q, True) if t in o.vocab]
+
+
+def test_tokeniser_matches_oracle():
+    from hybrid_search_engine_b200 import extractor as ex
+    assert ex.STOPWORDS == orc.STOPWORDS
+    for s in ["", "The Quick-brown_fox's 2nd naïve café", "  a\tb\n c  ", "ÀB ſ İx", "the and of"]:
+        for rs in (False, True):
+            assert ex.extract_tokens(s, rs) == orc.extract_tokens(s, rs)
+        assert ex.preprocess_text(s) == orc.preprocess_text(s)
+    assert ex.extract_tokens("naïve café") == ["na", "ve", "caf"]
+
+
+def test_synth_is_deterministic_and_well_formed():
+    from hybrid_search_engine_b200 import synth
+    spec = synth.SynthSpec(n_docs=1000, vocab=500, dim=64, min_len=5, max_len=20)
+    a = synth.embeddings(spec, 10, 20)
+    assert np.array_equal(a, synth.embeddings(spec, 0, 30)[10:20])          # counter based: slice-invariant
+    assert abs(float(synth.embeddings(spec, 0, 1000).std()) - 1.0) < 0.02
+    dl, terms = synth.doc_tokens(spec, 0, 1000)
+    assert dl.min() >= 5 and dl.max() <= 20 and terms.max() < 500
+    dl2, terms2 = synth.doc_tokens(spec, 500, 1000)
+    assert np.array_equal(terms2, terms[dl[:500].sum():])
+    th = synth.zipf_thresholds(500)
+    assert np.all(th[1:] >= th[:-1]) and th[-1] == np.uint64(0xFFFFFFFFFFFFFFFF)
+    # streams of different seeds do not alias (the bug class the seed scrambling prevents)
+    assert synth.query_texts(spec, 0, 8) != synth.doc_texts(spec, 0, 8)
+    assert not np.array_equal(synth.query_embeddings(spec, 0, 8), synth.embeddings(spec, 0, 8))
