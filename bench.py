@@ -223,7 +223,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident timing: upload once per step OUTSIDE the timed events
-    def device_step(qd, qt, qi, qo, timers=None):
+    def device_step(qd, qt, qi, qo, n_tok, timers=None):
         stats = eng._stats(B)
         if timers is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -232,7 +232,7 @@ def run_ours(args):
         if timers is not None:
             e1.record()
             timers.append((e0, e1))
-        bm = eng.bm25_score(qt, qi, qo, B, stats)
+        bm = eng.bm25_score(qt, qi, qo, B, stats, n_tok)
         stats = eng._exchange_stats(stats, B)
         keys = eng.fuse_topk(2, cos, bm, stats, 0.6, 0.4, k)
         return eng.unpack(keys)
@@ -242,7 +242,7 @@ def run_ours(args):
         qb = batch_of(s)
         qd = eng.upload_vectors(qb.vectors).clone()
         qt, qi, qo = [t.clone() for t in eng.upload_terms(qb.term_ids)]
-        staged.append((qd, qt, qi, qo))
+        staged.append((qd, qt, qi, qo, eng._n_tokens))
     for s in range(args.warmup):
         device_step(*staged[s])
     barrier()

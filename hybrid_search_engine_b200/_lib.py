@@ -29,15 +29,16 @@ SIGNATURES = {
     "hs_index_destroy": (C.c_int, [_vp]),
     "hs_index_set_dense": (C.c_int, [_vp, _vp, _i32, _i64, _vp]),
     "hs_index_set_csr": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),
-    "hs_index_set_doc_stats": (C.c_int, [_vp, _vp, _f64, _f64, _f64, _vp, _u32]),
+    "hs_index_set_doc_stats": (C.c_int, [_vp, _vp, _f64, _f64, _f64, _vp, _u32, _u32]),
     "hs_row_norms": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp]),
-    "hs_bm25_kd_table": (C.c_int, [_f64, _f64, _f64, _u32, _vp, _vp]),
+    "hs_bm25_impact_table": (C.c_int, [_f64, _f64, _f64, _u32, _u32, _vp, _vp]),
     "hs_stats_reset": (C.c_int, [_vp, _i32, _vp]),
     "hs_stats_decode": (C.c_int, [_vp, _vp, _i32, _vp]),
     "hs_stats_encode": (C.c_int, [_vp, _vp, _i32, _vp]),
     "hs_stats_fold_minmax": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "hs_dense_scan": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
-    "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "hs_bm25_workspace_bytes": (_sz, [_i64, _i32]),
+    "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "hs_fuse_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "hs_fuse_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),

@@ -72,15 +72,16 @@ int hs_index_set_csr(hs_index* idx, const int64_t* indptr, const uint32_t* posti
 }
 
 int hs_index_set_doc_stats(hs_index* idx, const uint32_t* dl, double avgdl, double k1, double b,
-                           const double* kd_table, uint32_t max_dl) {
+                           const double* impact_table, uint32_t max_dl, uint32_t tf_cap) {
     HS_REQUIRE(idx != nullptr, "hs_index_set_doc_stats: idx is null");
     HS_REQUIRE(dl != nullptr || idx->n_docs == 0, "hs_index_set_doc_stats: dl is null");
     idx->dl = dl;
     idx->avgdl = avgdl;
     idx->k1 = k1;
     idx->b = b;
-    idx->kd_table = kd_table;
+    idx->impact_table = impact_table;
     idx->max_dl = max_dl;
+    idx->tf_cap = tf_cap;
     return HS_OK;
 }
 

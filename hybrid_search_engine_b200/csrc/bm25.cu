@@ -13,8 +13,9 @@
 //     read-modify-write; __syncthreads() between tokens keeps the reference's float64 summation order.
 //   * arithmetic is the reference's, float64, no FMA contraction (bm25.py:104-110):
 //         num = tf * (k1 + 1); den = tf + k1 * (1 - b + b * (dl / avgdl)); score += idf * (num / den)
-//     k1 * (...) depends on dl only and comes from a float64 table indexed by dl (hs_bm25_kd_table),
-//     or is computed inline when no table was given.
+//     the fraction num / den depends on the small integers (dl, tf) only and is gathered from a float64
+//     table built once per index with the same instructions (hs_bm25_impact_table); pairs outside
+//     the table are computed inline.
 //   * epilogue: single rounding to float32 (bm25.py:124-126), coalesced store, tile max folded into
 //     stats slot HS_STAT_MAX_B (pipelines.py:332).
 //
@@ -26,14 +27,15 @@ namespace {
 constexpr int kTileDocs = 4096;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kTermGroup = 32;   // query tokens resolved per search round
+constexpr int kTermGroup = 32;
+constexpr int kUnroll = 8;        // postings in flight per thread   // query tokens resolved per search round
 
 struct Bm25Params {
     const int64_t* indptr;
     const uint2* postings;
     const uint32_t* dl;
-    const double* kd_table;
-    uint32_t max_dl;
+    const double* impact_table;
+    uint32_t max_dl, tf_cap;
     double k1, one_minus_b, b, avgdl, k1p1;
     const int32_t* q_terms;
     const double* q_idf;
@@ -41,12 +43,26 @@ struct Bm25Params {
     int64_t n_docs, n_terms;
     float* scores;        // [B, n]
     uint32_t* stats;      // [B, 4] or null
+    int64_t* ranges;      // [n_tokens, n_tiles + 1] posting offsets at every tile boundary (workspace)
+    int n_tiles;
 };
 
-__device__ __forceinline__ double bm25_kd(const Bm25Params& p, uint32_t dl) {
-    if (p.kd_table != nullptr && dl <= p.max_dl) return __ldg(p.kd_table + dl);
-    // k1 * (1 - b + b * (dl / avgdl))   (bm25.py:108)
-    return __dmul_rn(p.k1, __dadd_rn(p.one_minus_b, __dmul_rn(p.b, __ddiv_rn((double)dl, p.avgdl))));
+// (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (dl / avgdl))), or 0 where the reference adds 0 (den <= 0):
+// float64, the reference's operation order, no contraction (bm25.py:107-110)
+__device__ __forceinline__ double bm25_frac_compute(double k1, double one_minus_b, double b, double avgdl,
+                                                    double k1p1, uint32_t tf_u, uint32_t dl) {
+    const double tf = (double)tf_u;
+    const double kd = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, __ddiv_rn((double)dl, avgdl))));
+    const double num = __dmul_rn(tf, k1p1);
+    const double den = __dadd_rn(tf, kd);
+    return den > 0.0 ? __ddiv_rn(num, den) : 0.0;
+}
+// The fraction depends on the small integers (dl, tf) only, so it is tabulated once per index with the
+// same instructions (hs_bm25_impact_table): the hot loop replaces two float64 divisions by one gather.
+__device__ __forceinline__ double bm25_frac(const Bm25Params& p, uint32_t tf, uint32_t dl) {
+    if (p.impact_table != nullptr && dl <= p.max_dl && tf <= p.tf_cap)
+        return __ldg(p.impact_table + (size_t)dl * (p.tf_cap + 1) + tf);
+    return bm25_frac_compute(p.k1, p.one_minus_b, p.b, p.avgdl, p.k1p1, tf, dl);
 }
 
 // first index in [lo, hi) whose doc id >= target; whole warp cooperates (32-ary search)
@@ -103,21 +119,14 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p)
         const int gn = (t_end - g0 < kTermGroup) ? (t_end - g0) : kTermGroup;
         if (tid == 0) s_any = 0;
         __syncthreads();
-        // ---- locate each token's posting slice for this doc range (one warp per token)
-        for (int t = warp; t < gn; t += kWarps) {
-            const int term = p.q_terms[g0 + t];
-            int64_t lo = 0, hi = 0;
-            if (term >= 0 && term < p.n_terms) {
-                const int64_t pl = p.indptr[term], ph = p.indptr[term + 1];
-                lo = warp_lower_bound(p.postings, pl, ph, (uint32_t)d_lo, lane);
-                hi = (d_hi >= p.n_docs) ? ph : warp_lower_bound(p.postings, lo, ph, (uint32_t)d_hi, lane);
-            }
-            if (lane == 0) {
-                rng_lo[t] = lo;
-                rng_hi[t] = hi;
-                s_idf[t] = p.q_idf[g0 + t];
-                if (hi > lo) s_any = 1;
-            }
+        // ---- each token's posting slice for this doc range was located by bm25_ranges_kernel
+        if (tid < gn) {
+            const int64_t* r = p.ranges + (int64_t)(g0 + tid) * (p.n_tiles + 1) + blockIdx.x;
+            const int64_t lo = r[0], hi = r[1];
+            rng_lo[tid] = lo;
+            rng_hi[tid] = hi;
+            s_idf[tid] = p.q_idf[g0 + tid];
+            if (hi > lo) s_any = 1;
         }
         __syncthreads();
         if (!s_any) continue;
@@ -130,13 +139,28 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p)
         for (int t = 0; t < gn; ++t) {
             const int64_t lo = rng_lo[t], hi = rng_hi[t];
             const double idf = s_idf[t];
-            for (int64_t i = lo + tid; i < hi; i += kThreads) {
-                const uint2 pt = __ldg(&p.postings[i]);
-                const int j = (int)(pt.x - (uint32_t)d_lo);
-                const double tf = (double)pt.y;
-                const double num = __dmul_rn(tf, p.k1p1);
-                const double den = __dadd_rn(tf, bm25_kd(p, sdl[j]));
-                if (den > 0.0) acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, __ddiv_rn(num, den)));
+            // batches of kUnroll postings per thread: all posting loads first, then all table gathers,
+            // then the shared-memory updates -- kUnroll independent requests in flight instead of a
+            // load -> gather -> update chain per posting (docs within one list are distinct, so the
+            // updates of a batch never collide)
+            for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kThreads * kUnroll) {
+                uint2 pt[kUnroll];
+                double fr[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const int64_t i = i0 + (int64_t)u * kThreads;
+                    pt[u] = (i < hi) ? __ldg(&p.postings[i]) : make_uint2(0xFFFFFFFFu, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    fr[u] = (pt[u].x != 0xFFFFFFFFu) ? bm25_frac(p, pt[u].y, sdl[pt[u].x - (uint32_t)d_lo]) : 0.0;
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    if (pt[u].x != 0xFFFFFFFFu) {
+                        const int j = (int)(pt[u].x - (uint32_t)d_lo);
+                        acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, fr[u]));
+                    }
+                }
             }
             __syncthreads();
         }
@@ -164,11 +188,33 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p)
     }
 }
 
-__global__ void kd_table_kernel(double avgdl, double k1, double one_minus_b, double b, uint32_t max_dl,
-                                double* kd) {
-    const uint32_t l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l <= max_dl)
-        kd[l] = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, __ddiv_rn((double)l, avgdl))));
+// One warp per (query token, tile boundary): offset of the first posting with doc id >= boundary * kTileDocs.
+// All searches of a batch run concurrently (one ~5-round latency chain in total) instead of serially
+// at the head of every tile CTA.
+__global__ void bm25_ranges_kernel(const Bm25Params p, int n_tokens) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t per = p.n_tiles + 1;
+    if (w >= (int64_t)n_tokens * per) return;
+    const int tok = (int)(w / per);
+    const int j = (int)(w - (int64_t)tok * per);
+    const int term = p.q_terms[tok];
+    int64_t r = 0;
+    if (term >= 0 && term < p.n_terms) {
+        const int64_t pl = p.indptr[term], ph = p.indptr[term + 1];
+        if (j == 0) r = pl;
+        else if (j == p.n_tiles) r = ph;
+        else r = warp_lower_bound(p.postings, pl, ph, (uint32_t)((int64_t)j * kTileDocs), lane);
+    }
+    if (lane == 0) p.ranges[w] = r;
+}
+
+__global__ void impact_table_kernel(double avgdl, double k1, double one_minus_b, double b, double k1p1,
+                                    uint32_t max_dl, uint32_t tf_cap, double* table) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t w = tf_cap + 1;
+    if (i < (uint64_t)(max_dl + 1) * w)
+        table[i] = bm25_frac_compute(k1, one_minus_b, b, avgdl, k1p1, (uint32_t)(i % w), (uint32_t)(i / w));
 }
 
 // BM25.score for selected docs (multi_stage stage 2, pipelines.py:485): one warp per (query, candidate);
@@ -182,7 +228,7 @@ __global__ void bm25_docs_kernel(const Bm25Params p, const int64_t* __restrict__
     const int64_t doc = doc_ids[w];
     double score = 0.0;
     if (doc >= 0 && doc < p.n_docs) {
-        const double kd = bm25_kd(p, p.dl[doc]);
+        const uint32_t dl = p.dl[doc];
         for (int t = p.q_off[b]; t < p.q_off[b + 1]; ++t) {
             const int term = p.q_terms[t];
             if (term < 0 || term >= p.n_terms) continue;
@@ -190,12 +236,8 @@ __global__ void bm25_docs_kernel(const Bm25Params p, const int64_t* __restrict__
             const int64_t pos = warp_lower_bound(p.postings, pl, ph, (uint32_t)doc, lane);
             if (pos < ph) {
                 const uint2 pt = __ldg(&p.postings[pos]);
-                if (pt.x == (uint32_t)doc) {
-                    const double tf = (double)pt.y;
-                    const double num = __dmul_rn(tf, p.k1p1);
-                    const double den = __dadd_rn(tf, kd);
-                    if (den > 0.0) score = __dadd_rn(score, __dmul_rn(p.q_idf[t], __ddiv_rn(num, den)));
-                }
+                if (pt.x == (uint32_t)doc)
+                    score = __dadd_rn(score, __dmul_rn(p.q_idf[t], bm25_frac(p, pt.y, dl)));
             }
         }
     }
@@ -212,8 +254,9 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     p.indptr = idx->indptr;
     p.postings = idx->postings;
     p.dl = idx->dl;
-    p.kd_table = idx->kd_table;
+    p.impact_table = idx->impact_table;
     p.max_dl = idx->max_dl;
+    p.tf_cap = idx->tf_cap;
     p.k1 = idx->k1;
     p.b = idx->b;
     p.one_minus_b = 1 - idx->b;          // python: 1 - self.b
@@ -226,6 +269,8 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     p.n_terms = idx->n_terms;
     p.scores = nullptr;
     p.stats = nullptr;
+    p.ranges = nullptr;
+    p.n_tiles = (int)((idx->n_docs + kTileDocs - 1) / kTileDocs);
     return HS_OK;
 }
 
@@ -233,24 +278,41 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
 
 extern "C" {
 
-int hs_bm25_kd_table(double avgdl, double k1, double b, uint32_t max_dl, double* kd, void* stream) {
-    HS_REQUIRE(kd != nullptr, "hs_bm25_kd_table: kd is null");
-    const uint32_t n = max_dl + 1;
-    kd_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(avgdl, k1, 1 - b, b, max_dl, kd);
+int hs_bm25_impact_table(double avgdl, double k1, double b, uint32_t max_dl, uint32_t tf_cap, double* table,
+                         void* stream) {
+    HS_REQUIRE(table != nullptr, "hs_bm25_impact_table: table is null");
+    const uint64_t n = (uint64_t)(max_dl + 1) * (tf_cap + 1);
+    HS_REQUIRE(n <= (1ull << 31), "hs_bm25_impact_table: table too large");
+    impact_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(avgdl, k1, 1 - b, b, k1 + 1,
+                                                                                       max_dl, tf_cap, table);
     HS_LAUNCH_CHECK();
     return HS_OK;
 }
 
+size_t hs_bm25_workspace_bytes(int64_t n_docs, int32_t n_tokens) {
+    if (n_docs <= 0 || n_tokens <= 0) return 0;
+    return (size_t)n_tokens * (size_t)((n_docs + kTileDocs - 1) / kTileDocs + 1) * sizeof(int64_t);
+}
+
 int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
-                  int32_t B, float* scores, uint32_t* stats_enc, void* stream) {
+                  int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
+                  uint32_t* stats_enc, void* stream) {
     HS_REQUIRE(idx != nullptr, "hs_bm25_score: idx is null");
     if (idx->n_docs == 0 || B == 0) return HS_OK;
-    HS_REQUIRE(B > 0 && B <= 65535 && scores != nullptr, "hs_bm25_score: bad arguments (B=%d)", B);
+    HS_REQUIRE(B > 0 && B <= 65535 && scores != nullptr && n_tokens >= 0, "hs_bm25_score: bad arguments (B=%d)", B);
     Bm25Params p;
     int rc = fill_params(idx, q_terms, q_idf, q_off, p, "hs_bm25_score");
     if (rc != HS_OK) return rc;
     p.scores = scores;
     p.stats = stats_enc;
+    if (n_tokens > 0) {
+        HS_REQUIRE(workspace != nullptr && workspace_bytes >= hs_bm25_workspace_bytes(idx->n_docs, n_tokens),
+                   "hs_bm25_score: workspace too small");
+        p.ranges = (int64_t*)workspace;
+        const int64_t warps = (int64_t)n_tokens * (p.n_tiles + 1);
+        bm25_ranges_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n_tokens);
+        HS_LAUNCH_CHECK();
+    }
     dim3 grid((unsigned)((idx->n_docs + kTileDocs - 1) / kTileDocs), (unsigned)B);
     const size_t smem = (size_t)kTileDocs * (sizeof(double) + sizeof(uint32_t));
     HS_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -26,8 +26,9 @@ struct hs_index {
     int64_t n_postings = 0;
     // doc stats
     const uint32_t* dl = nullptr;
-    const double* kd_table = nullptr;
+    const double* impact_table = nullptr;   // [(max_dl + 1) * (tf_cap + 1)], see hs_bm25_impact_table
     uint32_t max_dl = 0;
+    uint32_t tf_cap = 0;
     double avgdl = 0.0, k1 = 1.5, b = 0.75;
 };
 

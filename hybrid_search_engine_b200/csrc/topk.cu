@@ -47,10 +47,36 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* a) {
     }
 }
 
+// same network over the first n (power of two) entries only
+__device__ __forceinline__ void bitonic_sort_desc_n(uint64_t* a, int n) {
+    const int tid = threadIdx.x;
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < n / 2; i += kThreads) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t x = a[lo], y = a[hi];
+                if ((x < y) == desc) {
+                    a[lo] = y;
+                    a[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // Streaming top-k state in shared memory.
+//
+// `shared_thr` (optional, global memory, one per query) lets all CTAs working on the same query pool
+// their knowledge: whenever a CTA has k real keys, its k-th best is a lower bound on the GLOBAL k-th
+// best, so it is published with atomicMax and every CTA filters with max(own, published).  CTAs that
+// start late then append almost nothing; their output is "every key of my range above the published
+// bound", still a superset of (global top k) restricted to the range, which is all the merge needs.
 template <int KP>
 struct Selector {
-    static constexpr int CAP = 2 * KP;
+    static constexpr int CAP = (KP <= 128) ? 8 * KP : 2 * KP;
     uint64_t buf[CAP];
     uint64_t thr;   // keys <= thr cannot be in the top k any more
     int cnt;        // next free slot (>= KP: slots [0, KP) hold the current best)
@@ -63,25 +89,41 @@ struct Selector {
         }
         __syncthreads();
     }
+    __device__ __forceinline__ uint64_t bound(const unsigned long long* shared_thr) const {
+        uint64_t t = thr;
+        if (shared_thr != nullptr) {
+            const uint64_t g = *reinterpret_cast<const volatile unsigned long long*>(shared_thr);
+            if (g > t) t = g;
+        }
+        return t;
+    }
     // all threads call with their kItems keys (0 = nothing).  Collective.
-    __device__ void push(uint64_t (&key)[kItems], int k) {
+    __device__ void push(uint64_t (&key)[kItems], int k, unsigned long long* shared_thr = nullptr) {
+        const int lane = threadIdx.x & 31;
         unsigned pend = 0;
 #pragma unroll
         for (int j = 0; j < kItems; ++j)
             if (key[j] != 0) pend |= 1u << j;
         while (true) {
-            const uint64_t t = thr;
+            const uint64_t t = bound(shared_thr);
 #pragma unroll
             for (int j = 0; j < kItems; ++j) {
-                if (pend & (1u << j)) {
-                    if (key[j] > t) {
-                        const int pos = atomicAdd(&cnt, 1);
+                const bool live = (pend >> j) & 1u;
+                const bool want = live && key[j] > t;
+                if (live && !want) pend &= ~(1u << j);
+                // warp-aggregated append: one shared atomic per warp and item slot
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, want);
+                if (m != 0) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&cnt, __popc(m));
+                    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                    if (want) {
+                        const int pos = base + __popc(m & ((1u << lane) - 1u));
                         if (pos < CAP) {
                             buf[pos] = key[j];
                             pend &= ~(1u << j);
                         }
-                    } else {
-                        pend &= ~(1u << j);
                     }
                 }
             }
@@ -89,19 +131,30 @@ struct Selector {
             // is the (block-uniform) prune condition
             const int more = __syncthreads_or(pend != 0);
             if (!more) break;
-            prune(k);
+            prune(k, shared_thr);
         }
     }
     // collective: sort, keep the best KP, raise the threshold to the k-th best
-    __device__ void prune(int k) {
+    __device__ void prune(int k, unsigned long long* shared_thr = nullptr) {
         bitonic_sort_desc<CAP>(buf);
         if (threadIdx.x == 0) {
-            thr = buf[k - 1];
+            const uint64_t kth = buf[k - 1];
+            thr = kth;
             cnt = KP;
+            if (shared_thr != nullptr && kth != 0) atomicMax(shared_thr, (unsigned long long)kth);
         }
         __syncthreads();
     }
-    __device__ void finish(int k) { prune(k); }
+    // final ordering: only slots [0, cnt) can hold keys that matter (slots beyond were discarded by an
+    // earlier prune), so sort the smallest power of two covering them
+    __device__ void finish(int k) {
+        int used = cnt < CAP ? cnt : CAP;
+        int n = KP;
+        while (n < used) n <<= 1;
+        for (int i = used + threadIdx.x; i < n; i += kThreads) buf[i] = 0;   // stale keys below the cut
+        __syncthreads();
+        bitonic_sort_desc_n(buf, n);
+    }
 };
 
 struct FuseParams {
@@ -110,7 +163,8 @@ struct FuseParams {
     const uint32_t* stats;
     const uint64_t* below;
     uint64_t* cand;       // [B, n_chunks, k]
-    int64_t n, doc_base;
+    unsigned long long* gthr;   // [B] published lower bounds on the k-th best key (zeroed per call)
+    int64_t n, doc_base, pilot_docs;
     int mode, k, n_chunks;
     float wa32, wb32;
     double wa64;
@@ -119,12 +173,16 @@ struct FuseParams {
 struct FuseConsts {
     float min_a, range_a, max_b_div, min_b, range_b;
     bool const_a, const_b;
+    // cheap upper-bound path: reciprocals for a multiply-only estimate of the fused score, and the
+    // margin that covers its distance from the exactly rounded value
+    float rcp_a, rcp_b, delta;
 };
 
 __device__ __forceinline__ FuseConsts load_consts(const FuseParams& p, int b) {
     FuseConsts c;
     c.min_a = c.range_a = c.max_b_div = c.min_b = c.range_b = 0.f;
     c.const_a = c.const_b = false;
+    c.rcp_a = c.rcp_b = c.delta = 0.f;
     if (p.mode == HS_FUSE_RAW) return c;
     const uint32_t* s = p.stats + b * 4;
     const float mn = hs_dec_f32(s[HS_STAT_MIN_A]), mx = hs_dec_f32(s[HS_STAT_MAX_A]);
@@ -140,7 +198,22 @@ __device__ __forceinline__ FuseConsts load_consts(const FuseParams& p, int b) {
         c.range_b = __fsub_rn(mxb, mnb);
         c.const_b = (c.range_b == 0.0f);
     }
+    c.rcp_a = c.const_a ? 0.f : 1.0f / c.range_a;
+    if (p.mode == HS_FUSE_HYBRID_BM25) c.rcp_b = 1.0f / c.max_b_div;
+    else c.rcp_b = (p.b == nullptr || c.const_b) ? 0.f : 1.0f / c.range_b;
+    // both normalised terms lie in [0, 1]; each estimate is within a few ulp of the exact value
+    c.delta = 8e-6f * (fabsf(p.wa32) + fabsf(p.wb32)) + 1e-30f;
     return c;
+}
+
+// Multiply-only estimate of fuse_score: |estimate - exact| < c.delta.  Used only to REJECT elements that
+// cannot reach the current threshold; everything else goes through the exact path.
+__device__ __forceinline__ float fuse_score_estimate(const FuseParams& p, const FuseConsts& c, float a, float b) {
+    const float an = c.const_a ? 1.0f : (a - c.min_a) * c.rcp_a;
+    float bn;
+    if (p.mode == HS_FUSE_HYBRID_BM25) bn = b * c.rcp_b;
+    else bn = (p.b == nullptr) ? 0.f : (c.const_b ? 1.0f : (b - c.min_b) * c.rcp_b);
+    return an * p.wa32 + bn * p.wb32;
 }
 
 __device__ __forceinline__ float fuse_score(const FuseParams& p, const FuseConsts& c, float a, float b) {
@@ -163,14 +236,17 @@ __device__ __forceinline__ float fuse_score(const FuseParams& p, const FuseConst
     return __fadd_rn(t1, t2);
 }
 
-template <int KP>
+// PILOT = true: one CTA per query scans only the first p.pilot_docs docs and publishes the k-th best key
+// of that sample as the starting bound (a subset's k-th best is a valid lower bound), so the CTAs of the
+// main launch reject almost everything with the cheap estimate and rarely need to sort.
+template <int KP, bool PILOT>
 __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p) {
     __shared__ Selector<KP> sel;
     const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
     const int64_t span = ((p.n + p.n_chunks - 1) / p.n_chunks + kThreads * kItems - 1) / (kThreads * kItems) *
                          (kThreads * kItems);
-    const int64_t lo = (int64_t)chunk * span;
-    const int64_t hi = (lo + span < p.n) ? lo + span : p.n;
+    const int64_t lo = PILOT ? 0 : (int64_t)chunk * span;
+    const int64_t hi = PILOT ? p.pilot_docs : ((lo + span < p.n) ? lo + span : p.n);
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
     const float* pa = p.a + (int64_t)b * p.n;
@@ -185,16 +261,24 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
             av[j] = (i < hi) ? __ldg(pa + i) : 0.f;
             bv[j] = (pb != nullptr && i < hi) ? __ldg(pb + i) : 0.f;
         }
+        // score the current bound stands for (bound 0 = nothing known yet -> -inf)
+        const uint64_t t = sel.bound(p.gthr + b);
+        const float thr_f = (t == 0) ? __int_as_float(0xff800000) : hs_dec_f32((uint32_t)(t >> 32));
 #pragma unroll
         for (int j = 0; j < kItems; ++j) {
             const int64_t i = base + j * kThreads + tid;
             key[j] = 0;
             if (i < hi) {
+                if (p.mode != HS_FUSE_RAW && fuse_score_estimate(p, c, av[j], bv[j]) + c.delta < thr_f) continue;
                 const uint64_t kk = hs_make_key(fuse_score(p, c, av[j], bv[j]), (uint32_t)(p.doc_base + i));
                 if (kk < below) key[j] = kk;
             }
         }
-        sel.push(key, p.k);
+        sel.push(key, p.k, p.gthr + b);
+    }
+    if (PILOT) {
+        if (sel.cnt > KP) sel.prune(p.k, p.gthr + b);     // publishes the sample's k-th best (if it has k keys)
+        return;
     }
     sel.finish(p.k);
     uint64_t* out = p.cand + ((int64_t)b * p.n_chunks + chunk) * p.k;
@@ -227,6 +311,47 @@ __global__ void __launch_bounds__(kThreads) topk_merge_kernel(const uint64_t* __
     for (int i = tid; i < k; i += kThreads) out[(int64_t)b * k + i] = sel.buf[i];
 }
 
+// Same contract as topk_merge_kernel for MANY lists (the per-CTA candidate lists of fuse_topk_kernel):
+// every list is sorted descending, so thread t walks list t (and t + 256, ...) from the top and stops
+// at the first key that is not above the running threshold.  The number of rounds is the deepest any
+// list reaches into the final top k (a handful for random data), not n_lists * k / 1024.
+template <int KP>
+__global__ void __launch_bounds__(kThreads) topk_merge_walk_kernel(const uint64_t* __restrict__ keys, int n_lists,
+                                                                   int B, int k, int64_t list_stride,
+                                                                   int64_t query_stride, uint64_t* __restrict__ out) {
+    __shared__ Selector<KP> sel;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    sel.init();
+    int pos[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) pos[j] = (j * kThreads + tid < n_lists) ? 0 : k;
+    // requires n_lists <= kItems * kThreads (the dispatcher falls back to the flat kernel otherwise)
+    while (true) {
+        uint64_t key[kItems];
+        const uint64_t t = sel.thr;
+        int any = 0;
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            key[j] = 0;
+            if (pos[j] < k) {
+                const int l = j * kThreads + tid;
+                const uint64_t kk = keys[l * list_stride + (int64_t)b * query_stride + pos[j]];
+                if (kk > t) {
+                    key[j] = kk;
+                    ++pos[j];
+                    any = 1;
+                } else {
+                    pos[j] = k;      // sorted: nothing further down this list can qualify
+                }
+            }
+        }
+        if (!__syncthreads_or(any)) break;
+        sel.push(key, k);
+    }
+    sel.finish(k);
+    for (int i = tid; i < k; i += kThreads) out[(int64_t)b * k + i] = sel.buf[i];
+}
+
 int n_chunks_for(int64_t n) {
     int64_t c = (n + kChunkDocs - 1) / kChunkDocs;
     if (c < 1) c = 1;
@@ -237,7 +362,10 @@ int n_chunks_for(int64_t n) {
 template <int KP>
 int launch_merge(const uint64_t* keys, int n_lists, int B, int k, int64_t list_stride, int64_t query_stride,
                  uint64_t* out, cudaStream_t st) {
-    topk_merge_kernel<KP><<<B, kThreads, 0, st>>>(keys, n_lists, B, k, list_stride, query_stride, out);
+    if (n_lists >= 32 && n_lists <= kItems * kThreads)
+        topk_merge_walk_kernel<KP><<<B, kThreads, 0, st>>>(keys, n_lists, B, k, list_stride, query_stride, out);
+    else
+        topk_merge_kernel<KP><<<B, kThreads, 0, st>>>(keys, n_lists, B, k, list_stride, query_stride, out);
     HS_LAUNCH_CHECK();
     return HS_OK;
 }
@@ -255,7 +383,7 @@ extern "C" {
 
 size_t hs_fuse_topk_workspace_bytes(int64_t n_docs, int32_t B, int32_t k) {
     if (n_docs <= 0 || B <= 0 || k <= 0) return 0;
-    return (size_t)B * n_chunks_for(n_docs) * (size_t)k * sizeof(uint64_t);
+    return ((size_t)B * n_chunks_for(n_docs) * (size_t)k + (size_t)B) * sizeof(uint64_t);
 }
 
 int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const float* b,
@@ -286,7 +414,9 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
     p.b = b;
     p.stats = stats_enc;
     p.below = below_key;
-    p.cand = (uint64_t*)workspace;
+    p.gthr = (unsigned long long*)workspace;
+    p.cand = (uint64_t*)workspace + B;
+    HS_CUDA(cudaMemsetAsync(p.gthr, 0, (size_t)B * sizeof(uint64_t), st));
     p.n = idx->n_docs;
     p.doc_base = idx->doc_base;
     p.mode = fuse_mode;
@@ -296,12 +426,22 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
     p.wb32 = (float)w_b;
     p.wa64 = w_a;
     dim3 grid((unsigned)p.n_chunks, (unsigned)B);
+    // pilot pass over a small prefix when the corpus is large enough for it to pay (see the kernel)
+    p.pilot_docs = (idx->n_docs >= (int64_t)64 * 16384 && k <= 512) ? 16384 : 0;
+    if (p.pilot_docs > 0) {
+        dim3 pg(1, (unsigned)B);
+        if (k <= 128)
+            fuse_topk_kernel<128, true><<<pg, kThreads, 0, st>>>(p);
+        else
+            fuse_topk_kernel<512, true><<<pg, kThreads, 0, st>>>(p);
+        HS_LAUNCH_CHECK();
+    }
     if (k <= 128)
-        fuse_topk_kernel<128><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<128, false><<<grid, kThreads, 0, st>>>(p);
     else if (k <= 512)
-        fuse_topk_kernel<512><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<512, false><<<grid, kThreads, 0, st>>>(p);
     else
-        fuse_topk_kernel<2048><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<2048, false><<<grid, kThreads, 0, st>>>(p);
     HS_LAUNCH_CHECK();
     // candidate layout [B, n_chunks, k]: list stride k, query stride n_chunks * k
     return merge_dispatch(p.cand, p.n_chunks, B, k, (int64_t)k, (int64_t)p.n_chunks * k, out_keys, st);

@@ -109,6 +109,7 @@ class SearchEngine:
         d_t.copy_(pin_t, non_blocking=True)
         d_i.copy_(pin_i, non_blocking=True)
         d_o.copy_(pin_o, non_blocking=True)
+        self._n_tokens = T          # host copy of q_off[B] for the kernel's workspace sizing
         return d_t, d_i, d_o
 
     # ------------------------------------------------------------------ kernels
@@ -130,24 +131,32 @@ class SearchEngine:
     def dense_launches(self, B: int, mode: Optional[str] = None) -> int:
         nchunk = (self.shard.dim + 127) // 128
         nchunk = nchunk if nchunk <= 4 else (6 if nchunk <= 6 else 8)
-        budget, cap = (12, 4) if (mode or self.dense_mode) == "exact" else (24, 8)
+        budget, cap = (6, 2) if (mode or self.dense_mode) == "exact" else (12, 4)
         bq = 1
         while bq * 2 <= budget // nchunk and bq * 2 <= cap:
             bq *= 2
         n, b = 0, B
-        while b > 0:
+        while b > 0:               # mirrors hs_dense_scan: BQ queries per warp x QG warps per stage
             step = bq
             while step > b:
                 step //= 2
-            b -= step
+            qg = 4
+            while qg > 1 and step * qg > b:
+                qg //= 2
+            b -= step * qg
             n += 1
         return n
 
-    def bm25_score(self, q_terms, q_idf, q_off, B: int, stats: Optional[torch.Tensor]) -> torch.Tensor:
+    def bm25_score(self, q_terms, q_idf, q_off, B: int, stats: Optional[torch.Tensor],
+                   n_tokens: Optional[int] = None) -> torch.Tensor:
+        n_tokens = self._n_tokens if n_tokens is None else int(n_tokens)
         sc = self._buf("bm25", (B, self.shard.n_docs), torch.float32)
-        check(self.lib.hs_bm25_score(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, ptr(sc),
-                                     ptr(stats), stream_ptr(self.device)), "hs_bm25_score")
-        self.launches += 1
+        nbytes = self.lib.hs_bm25_workspace_bytes(self.shard.n_docs, n_tokens)
+        ws = self._buf("bm25_ws", (max(nbytes // 8, 1),), torch.int64)
+        check(self.lib.hs_bm25_score(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, n_tokens,
+                                     ptr(ws), nbytes, ptr(sc), ptr(stats), stream_ptr(self.device)),
+              "hs_bm25_score")
+        self.launches += 2 if n_tokens > 0 else 1
         return sc
 
     def _exchange_stats(self, stats: torch.Tensor, B: int) -> torch.Tensor:

@@ -7,7 +7,7 @@ HBM layout of one shard (docs ``doc_base .. doc_base + n_docs - 1``):
     indptr    int64   [n_terms + 1]     CSR over GLOBAL term ids, restricted to this shard's docs
     postings  uint32  [n_postings, 2]   (doc_id local to the shard, tf), doc ids ascending per term
     dl        uint32  [n_docs]          tokens after stop-word removal (bm25.py:59-60)
-    kd_table  float64 [max_dl + 1]      k1 * (1 - b + b * dl / avgdl) per possible doc length
+    impact    float64 [max_dl+1, tf_cap+1]  tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl)) per (doc length, tf)
     idf       float64 [n_terms]         host copy too; ln((N - df + .5) / (df + .5) + 1) (bm25.py:81)
 
 Corpus-global statistics (N, df -> idf, avgdl) are replicated on every shard.
@@ -55,7 +55,7 @@ class DeviceIndex:
         self.dim = 0
         self.ld = 0
         self.vectors = self.vnorm = None
-        self.indptr = self.postings = self.dl = self.kd_table = None
+        self.indptr = self.postings = self.dl = self.impact_table = None
         self.n_terms = 0
         self.avgdl = 0.0
         self.k1, self.b = 1.5, 0.75
@@ -108,15 +108,19 @@ class DeviceIndex:
         self.max_dl = int(max_dl)
         with torch.cuda.device(self.device):
             st = stream_ptr(self.device)
-            self.kd_table = None
-            if avgdl > 0 and self.max_dl <= (1 << 22):
-                self.kd_table = torch.empty(self.max_dl + 1, dtype=torch.float64, device=self.device)
-                check(self.lib.hs_bm25_kd_table(float(avgdl), self.k1, self.b, self.max_dl,
-                                                ptr(self.kd_table), st), "hs_bm25_kd_table")
+            self.impact_table, self.tf_cap = None, 0
+            if avgdl > 0 and self.max_dl < (1 << 20):
+                # table of <= 8 MB: 31 tf columns for ordinary doc lengths, fewer for very long docs
+                self.tf_cap = 31 if self.max_dl < (1 << 15) else (7 if self.max_dl < (1 << 17) else 0)
+                self.impact_table = torch.empty((self.max_dl + 1) * (self.tf_cap + 1), dtype=torch.float64,
+                                                device=self.device)
+                check(self.lib.hs_bm25_impact_table(float(avgdl), self.k1, self.b, self.max_dl, self.tf_cap,
+                                                    ptr(self.impact_table), st), "hs_bm25_impact_table")
             check(self.lib.hs_index_set_csr(self.handle, ptr(self.indptr), ptr(self.postings), self.n_terms,
                                             self.postings.shape[0]), "hs_index_set_csr")
             check(self.lib.hs_index_set_doc_stats(self.handle, ptr(self.dl), float(avgdl), self.k1, self.b,
-                                                  ptr(self.kd_table), self.max_dl), "hs_index_set_doc_stats")
+                                                  ptr(self.impact_table), self.max_dl, self.tf_cap),
+                  "hs_index_set_doc_stats")
 
     @property
     def has_dense(self) -> bool:

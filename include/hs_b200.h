@@ -69,15 +69,18 @@ int hs_index_set_dense(hs_index* idx, const float* vectors, int32_t dim, int64_t
 int hs_index_set_csr(hs_index* idx, const int64_t* indptr, const uint32_t* postings, int64_t n_terms,
                      int64_t n_postings);
 /* doc lengths u32[n_docs] after stop-word removal (bm25.py:59-60), corpus-global avgdl (bm25.py:71),
- * k1, b (bm25.py:19-33); kd_table double[max_dl+1] from hs_bm25_kd_table or NULL to compute inline */
+ * k1, b (bm25.py:19-33); impact_table double[(max_dl+1) * (tf_cap+1)] from hs_bm25_impact_table, or
+ * NULL to compute every posting inline */
 int hs_index_set_doc_stats(hs_index* idx, const uint32_t* dl, double avgdl, double k1, double b,
-                           const double* kd_table, uint32_t max_dl);
+                           const double* impact_table, uint32_t max_dl, uint32_t tf_cap);
 
 /* ---- index-time kernels ------------------------------------------------------------------------ */
 /* vnorm[i] = f32(sqrt(sum64 v[i,:]^2)), conformance order (utils.py:47 np.linalg.norm per row) */
 int hs_row_norms(const float* vectors, int64_t n, int32_t dim, int64_t ld, float* vnorm, void* stream);
-/* kd[l] = k1 * ((1 - b) + b * (l / avgdl)) in float64, reference operation order (bm25.py:108) */
-int hs_bm25_kd_table(double avgdl, double k1, double b, uint32_t max_dl, double* kd, void* stream);
+/* table[dl * (tf_cap+1) + tf] = (tf * (k1+1)) / (tf + k1 * ((1-b) + b * (dl / avgdl))) in float64 with the
+ * reference's operation order (bm25.py:107-110); 0 where the reference adds 0 (denominator <= 0) */
+int hs_bm25_impact_table(double avgdl, double k1, double b, uint32_t max_dl, uint32_t tf_cap, double* table,
+                         void* stream);
 
 /* ---- hot path ---------------------------------------------------------------------------------- */
 /* stats: uint32[B][4] order-preserving encodings {min_a, max_a, max_b, min_b}; reset before a batch */
@@ -97,10 +100,12 @@ int hs_dense_scan(const hs_index* idx, const float* queries, int32_t B, int64_t 
 /* K1  BM25.score_batch (bm25.py:83-127) for B queries over the CSR: query b owns tokens
  *     q_off[b]..q_off[b+1]-1 (known terms only, query order, duplicates kept) with their float64 idf
  *     (bm25.py:81).  scores float32 [B, n_docs] (single rounding of the float64 sum, bm25.py:124-126);
- *     folds max into stats slot 2 (pipelines.py:332).  plus_delta < 0: Okapi; >= 0: BM25Plus is not
- *     sparse and is rejected here (see hs_bm25plus_... in a later ABI version). */
+ *     folds max into stats slot 2 (pipelines.py:332).  n_tokens = q_off[B] (host copy); workspace
+ *     holds the posting offsets of every token at every doc-tile boundary. */
+size_t hs_bm25_workspace_bytes(int64_t n_docs, int32_t n_tokens);
 int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
-                  int32_t B, float* scores, uint32_t* stats_enc, void* stream);
+                  int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
+                  uint32_t* stats_enc, void* stream);
 
 /* BM25.score (bm25.py:83-112) for selected docs only: multi_stage stage 2 (pipelines.py:485).
  * doc_ids int64 [B, C] (shard-local, < 0 = padding), out float64 [B, C], unrounded */
