@@ -57,8 +57,12 @@ def parse_args():
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    The sampler is started before the warm-up (nvidia-smi needs ~100 ms to come up) and samples every
+    20 ms; only samples stamped inside [mark_start, mark_end] -- the timed region -- are reported.
+    """
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -66,11 +70,12 @@ class ClockSampler:
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -78,28 +83,46 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def collect(lo, hi):
+            sm, smax, pw, reasons = [], [], [], set()
+            for ts, r in self.rows:
+                if not (lo <= ts <= hi):
+                    continue
+                f = [x.strip() for x in r.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, smax, pw, reasons
+
+        sm, smax, pw, reasons = collect(self.t0, self.t1)
+        window = "timed region"
+        if not sm:      # region shorter than one sampling period: widen by the sampling jitter
+            sm, smax, pw, reasons = collect(self.t0 - 0.1, self.t1 + 0.1)
+            window = "timed region +-100 ms (region shorter than the 20 ms sampling period)"
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------- CPU port
@@ -243,12 +266,13 @@ def run_ours(args):
         qd = eng.upload_vectors(qb.vectors).clone()
         qt, qi, qo = [t.clone() for t in eng.upload_terms(qb.term_ids)]
         staged.append((qd, qt, qi, qo, eng._n_tokens))
-    for s in range(args.warmup):
-        device_step(*staged[s])
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for s in range(args.warmup):
+        device_step(*staged[s])
+    barrier()
+    sampler.mark_start()
     launches0 = eng.launches
     timers = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -257,6 +281,7 @@ def run_ours(args):
         sc, ids = device_step(*staged[args.warmup + s], timers=timers)
     ev1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launches - launches0
     dev_ms = ev0.elapsed_time(ev1)
@@ -295,6 +320,12 @@ def run_ours(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         n_shard = hi - lo
         alg_bytes = n_shard * shard.ld * 4
+        traffic = None      # DRAM bytes per launch from the committed ncu --set full capture, if one matches
+        try:
+            ent = json.load(open(os.path.join(ROOT, "profiles", "dense_traffic.json")))["entries"]
+            traffic = ent.get(f"n{n_shard}_ld{shard.ld}_q{min(B, 8)}")
+        except Exception:
+            pass
         achieved = alg_bytes / (dense_ms / dense_launches_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": args.steps * B / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -312,7 +343,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": alg_bytes, "launch_ms": dense_ms / dense_launches_per_step,
                          "launches_per_step": dense_launches_per_step,
                          "dense_share_of_step": dense_ms / (dev_ms / args.steps)},

@@ -163,15 +163,11 @@ class SearchEngine:
         """C2: global (min, max) per query across shards -- one all-reduce(MAX) of B x 4 floats."""
         if self.group is None or self.world == 1:
             return stats
-        import torch.distributed as dist
+        from .parallel import allreduce_stats
         f = self._buf("stats_f", (B, 4), torch.float32)
         st = stream_ptr(self.device)
         check(self.lib.hs_stats_decode(ptr(stats), ptr(f), B, st), "hs_stats_decode")
-        f[:, 0].neg_()
-        f[:, 3].neg_()
-        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.group)
-        f[:, 0].neg_()
-        f[:, 3].neg_()
+        allreduce_stats(f, self.group)
         check(self.lib.hs_stats_encode(ptr(f), ptr(stats), B, st), "hs_stats_encode")
         self.launches += 2
         return stats
@@ -189,9 +185,8 @@ class SearchEngine:
               "hs_fuse_topk")
         self.launches += 2 if n > 0 else 0
         if self.group is not None and self.world > 1:
-            import torch.distributed as dist
-            gathered = self._buf("keys_all", (self.world, B, k), torch.int64)
-            dist.all_gather_into_tensor(gathered.view(-1), keys.view(-1), group=self.group)   # C1
+            from .parallel import allgather_keys
+            gathered = allgather_keys(keys, self.group, self._buf("keys_all", (self.world, B, k), torch.int64))  # C1
             merged = self._buf("keys_merged", (B, k), torch.int64)
             check(self.lib.hs_topk_merge(ptr(gathered), self.world, B, k, ptr(merged),
                                          stream_ptr(self.device)), "hs_topk_merge")
