@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=384)
     ap.add_argument("--batch", type=int, default=8, help="queries per step")
     ap.add_argument("--top-k", type=int, default=100)
-    ap.add_argument("--dense-mode", default="exact", choices=["exact", "fp32"])
+    ap.add_argument("--dense-mode", default="fp32", choices=["exact", "fp32"])
     ap.add_argument("--cpu-sample-docs", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -57,33 +57,51 @@ def parse_args():
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md).
 
-    The sampler is started before the warm-up (nvidia-smi needs ~100 ms to come up) and samples every
-    20 ms; only samples stamped inside [mark_start, mark_end] -- the timed region -- are reported.
+    In-process NVML polling every 5 ms (nvidia-smi's loop mode cannot sample a 50 ms region reliably);
+    only samples taken between mark_start() and mark_end() are reported.
     """
-    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
-        self.proc = None
         self.t0 = self.t1 = None
+        self._stop = False
+        self._thread = None
+        self._err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indices follow PCI order; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+            def loop():
+                while not self._stop:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.rows.append((time.time(), sm, pw, rs))
+                    except Exception as e:      # keep sampling; report the error once
+                        self._err = repr(e)
+                    time.sleep(0.005)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception as e:
+            self._err = repr(e)
 
     def mark_start(self):
         self.t0 = time.time()
@@ -92,37 +110,24 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-
-        def collect(lo, hi):
-            sm, smax, pw, reasons = [], [], [], set()
-            for ts, r in self.rows:
-                if not (lo <= ts <= hi):
-                    continue
-                f = [x.strip() for x in r.split(",")]
-                if len(f) < 8:
-                    continue
-                try:
-                    sm.append(float(f[1])); smax.append(float(f[2])); pw.append(float(f[3]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            return sm, smax, pw, reasons
-
-        sm, smax, pw, reasons = collect(self.t0, self.t1)
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [f"nvml unavailable: {self._err}"]}
+        inside = [r for r in self.rows if self.t0 <= r[0] <= self.t1]
         window = "timed region"
-        if not sm:      # region shorter than one sampling period: widen by the sampling jitter
-            sm, smax, pw, reasons = collect(self.t0 - 0.1, self.t1 + 0.1)
-            window = "timed region +-100 ms (region shorter than the 20 ms sampling period)"
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window,
-                "reasons": sorted(reasons)}
+        if not inside:
+            inside = [r for r in self.rows if self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
+            window = "timed region +-50 ms"
+        reasons = set()
+        for r in inside:
+            for bit, name in self.REASONS.items():
+                if r[3] & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None,
+                "sm_max_mhz": float(self._max), "power_w_max": max([r[2] for r in inside]) if inside else None,
+                "samples": len(inside), "window": window, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------- CPU port
@@ -309,6 +314,11 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX, group=group)
     e2e_s = float(te[0])
     same = bool(np.array_equal(res_ids.numpy(), last_ids))
+    # conformance check outside the timed regions: the same batch in the float64-accumulated `exact` dense
+    # mode (bit-identical to the CPU oracle in the parity tests) must give the same top-k ids
+    a, b_ = eng.search_hybrid_bm25(batch_of(args.warmup + args.steps - 1), k, 0.6, 0.4, dense_mode="exact")
+    exact_ids = b_.cpu().numpy()
+    ids_equal_exact = float(np.mean(exact_ids == res_ids.numpy()))
     h2d = B * args.dim * 4 + sum(len(x) for x in batch_of(0).term_ids) * 12 + (B + 1) * 4
     d2h = B * k * (4 + 8)
 
@@ -340,6 +350,8 @@ def run_ours(args):
                        "index_build_s": round(build_s, 1)},
             "e2e": {"value": args.steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "same_ids_as_device_run": same},
+            "parity": {"topk_ids_equal_to_exact_mode": ids_equal_exact,
+                       "note": "exact mode == CPU oracle bit for bit (tests/test_gpu_parity.py)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel", "achieved": achieved, "peak": peak,

@@ -28,7 +28,7 @@ constexpr int kTileDocs = 4096;
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTermGroup = 32;
-constexpr int kUnroll = 8;        // postings in flight per thread   // query tokens resolved per search round
+constexpr int kUnroll = 4;        // postings in flight per thread in the streaming part   // query tokens resolved per search round
 
 struct Bm25Params {
     const int64_t* indptr;
@@ -96,7 +96,13 @@ __device__ __forceinline__ int64_t warp_lower_bound(const uint2* __restrict__ po
     return r < hi ? r : hi;
 }
 
-__global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p) {
+// kPreTerms x kPreDepth postings per thread are fetched into registers for ALL leading tokens at once,
+// before the ordered accumulation starts: the CTA then pays one DRAM round trip for its postings instead
+// of one per token (the accumulation itself only touches shared memory and the small impact table).
+constexpr int kPreTerms = 4;
+constexpr int kPreDepth = 4;
+
+__global__ void __launch_bounds__(kThreads, 3) bm25_tile_kernel(const Bm25Params p) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
     double* acc = reinterpret_cast<double*>(bm25_smem);                       // [kTileDocs] float64 partial scores
     uint32_t* sdl = reinterpret_cast<uint32_t*>(acc + kTileDocs);             // [kTileDocs] staged doc lengths
@@ -106,8 +112,11 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p)
     __shared__ int s_any;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    const int64_t d_lo = (int64_t)blockIdx.x * kTileDocs;
+    // queries are the fastest grid index: the B CTAs of one doc tile run together and share its doc
+    // lengths through L2
+    const int b = blockIdx.x;
+    const int tile = blockIdx.y;
+    const int64_t d_lo = (int64_t)tile * kTileDocs;
     const int64_t d_hi = (d_lo + kTileDocs < p.n_docs) ? d_lo + kTileDocs : p.n_docs;
     const int ndoc = (int)(d_hi - d_lo);
     const int t_begin = p.q_off[b], t_end = p.q_off[b + 1];
@@ -121,7 +130,7 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p)
         __syncthreads();
         // ---- each token's posting slice for this doc range was located by bm25_ranges_kernel
         if (tid < gn) {
-            const int64_t* r = p.ranges + (int64_t)(g0 + tid) * (p.n_tiles + 1) + blockIdx.x;
+            const int64_t* r = p.ranges + (int64_t)(g0 + tid) * (p.n_tiles + 1) + tile;
             const int64_t lo = r[0], hi = r[1];
             rng_lo[tid] = lo;
             rng_hi[tid] = hi;
@@ -130,19 +139,51 @@ __global__ void __launch_bounds__(kThreads) bm25_tile_kernel(const Bm25Params p)
         }
         __syncthreads();
         if (!s_any) continue;
+        // ---- prefetch: postings of the leading tokens (registers) + the tile's doc lengths (smem)
+        uint2 pre[kPreTerms][kPreDepth];
+#pragma unroll
+        for (int t = 0; t < kPreTerms; ++t) {
+#pragma unroll
+            for (int u = 0; u < kPreDepth; ++u) {
+                pre[t][u] = make_uint2(0xFFFFFFFFu, 0u);
+                if (t < gn) {
+                    const int64_t i = rng_lo[t] + tid + (int64_t)u * kThreads;
+                    if (i < rng_hi[t]) pre[t][u] = __ldg(&p.postings[i]);
+                }
+            }
+        }
         if (!dl_staged) {
             for (int j = tid; j < ndoc; j += kThreads) sdl[j] = p.dl[d_lo + j];
             dl_staged = true;
             __syncthreads();
         }
-        // ---- accumulate token by token, in query order
+        // ---- accumulate token by token, in query order (bm25.py:99)
         for (int t = 0; t < gn; ++t) {
-            const int64_t lo = rng_lo[t], hi = rng_hi[t];
             const double idf = s_idf[t];
+            int64_t lo = rng_lo[t];
+            const int64_t hi = rng_hi[t];
+            if (t < kPreTerms) {
+                double fr[kPreDepth];
+#pragma unroll
+                for (int tt = 0; tt < kPreTerms; ++tt) {          // static register indexing
+                    if (tt == t) {
+#pragma unroll
+                        for (int u = 0; u < kPreDepth; ++u)
+                            fr[u] = (pre[tt][u].x != 0xFFFFFFFFu)
+                                        ? bm25_frac(p, pre[tt][u].y, sdl[pre[tt][u].x - (uint32_t)d_lo]) : 0.0;
+#pragma unroll
+                        for (int u = 0; u < kPreDepth; ++u) {
+                            if (pre[tt][u].x != 0xFFFFFFFFu) {
+                                const int j = (int)(pre[tt][u].x - (uint32_t)d_lo);
+                                acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, fr[u]));
+                            }
+                        }
+                    }
+                }
+                lo += (int64_t)kThreads * kPreDepth;              // the rest of a long slice streams below
+            }
             // batches of kUnroll postings per thread: all posting loads first, then all table gathers,
-            // then the shared-memory updates -- kUnroll independent requests in flight instead of a
-            // load -> gather -> update chain per posting (docs within one list are distinct, so the
-            // updates of a batch never collide)
+            // then the shared-memory updates (docs within one list are distinct: no collisions)
             for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kThreads * kUnroll) {
                 uint2 pt[kUnroll];
                 double fr[kUnroll];
@@ -313,7 +354,8 @@ int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_i
         bm25_ranges_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n_tokens);
         HS_LAUNCH_CHECK();
     }
-    dim3 grid((unsigned)((idx->n_docs + kTileDocs - 1) / kTileDocs), (unsigned)B);
+    HS_REQUIRE(p.n_tiles <= 65535, "hs_bm25_score: shard has more than 65535 doc tiles (%d)", p.n_tiles);
+    dim3 grid((unsigned)B, (unsigned)p.n_tiles);
     const size_t smem = (size_t)kTileDocs * (sizeof(double) + sizeof(uint32_t));
     HS_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     bm25_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);

@@ -16,18 +16,25 @@
 //     (division, store, min/max) lane-parallel.  The pairing of partial sums is exactly the
 //     butterfly's, so the result is bit-identical to it:
 //       EXACT: products/sums in float64 -> bit-identical to oracle/hybrid_oracle.py:cosine_exact
-//       FP32 : float32 FMA, same order  -> as precise as the reference's float32 BLAS dot
+//       FP32 : packed float32 FMAs (two partial sums per lane) -> as precise as the reference's float32 BLAS dot
 //   * epilogue fused: cos = f32(dot) / (f32|q| * f32|v|) with the reference's zero-norm rules
 //     (utils.py:44-50), per-query min/max folded into the stats slots (utils.py:67-68)
 //
 // Algorithmic bytes per launch: n_docs * ld * 4 (the corpus pass), independent of BQ.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kStages = kConsumerWarps;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;
+// two consumer warpgroups + one producer warpgroup (only one of its lanes works).  The register file is
+// split per SM sub-partition (16 K registers, 3 warps each here), so the kernel starts at <= 168
+// registers/thread and then moves registers from the producer group to the consumers with setmaxnreg.
+constexpr int kThreads = (kConsumerWarps + 4) * 32;
+constexpr int kConsumerRegs = 224;
+constexpr int kProducerRegs = 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -113,27 +120,42 @@ struct GroupSum<0, NCHUNK, BQ, EXACT> {
     static __device__ __forceinline__ void run(const float* __restrict__ tile, int64_t ld, int r0, int lane,
                                                const acc_t (&q)[BQ][NCHUNK][4], acc_t (&out)[BQ]) {
         const float* row = tile + (size_t)r0 * ld;
+        if constexpr (EXACT) {
 #pragma unroll
-        for (int i = 0; i < BQ; ++i) out[i] = (acc_t)0;
+            for (int i = 0; i < BQ; ++i) out[i] = 0.0;
 #pragma unroll
-        for (int c = 0; c < NCHUNK; ++c) {
-            const int e = c * 128 + lane * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < ld) v = *reinterpret_cast<const float4*>(row + e);
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int e = c * 128 + lane * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < ld) v = *reinterpret_cast<const float4*>(row + e);
 #pragma unroll
-            for (int i = 0; i < BQ; ++i) {
-                if constexpr (EXACT) {
+                for (int i = 0; i < BQ; ++i) {
                     out[i] = __fma_rn((double)v.x, q[i][c][0], out[i]);
                     out[i] = __fma_rn((double)v.y, q[i][c][1], out[i]);
                     out[i] = __fma_rn((double)v.z, q[i][c][2], out[i]);
                     out[i] = __fma_rn((double)v.w, q[i][c][3], out[i]);
-                } else {
-                    out[i] = __fmaf_rn(v.x, q[i][c][0], out[i]);
-                    out[i] = __fmaf_rn(v.y, q[i][c][1], out[i]);
-                    out[i] = __fmaf_rn(v.z, q[i][c][2], out[i]);
-                    out[i] = __fmaf_rn(v.w, q[i][c][3], out[i]);
                 }
             }
+        } else {
+            // float32 mode: packed two-wide FMAs (fma.rn.f32x2, SASS FFMA2) halve the issue slots of the
+            // inner loop; each lane keeps an (even j, odd j) pair of partial sums per query
+            float2 acc2[BQ];
+#pragma unroll
+            for (int i = 0; i < BQ; ++i) acc2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int e = c * 128 + lane * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e < ld) v = *reinterpret_cast<const float4*>(row + e);
+                const float2 vlo = make_float2(v.x, v.y), vhi = make_float2(v.z, v.w);
+#pragma unroll
+                for (int i = 0; i < BQ; ++i) {
+                    acc2[i] = __ffma2_rn(vlo, make_float2(q[i][c][0], q[i][c][1]), acc2[i]);
+                    acc2[i] = __ffma2_rn(vhi, make_float2(q[i][c][2], q[i][c][3]), acc2[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < BQ; ++i) out[i] = __fadd_rn(acc2[i].x, acc2[i].y);
         }
     }
 };
@@ -163,9 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1) dense_scan_kernel(const DensePara
     }
     __syncthreads();
 
-    if (warp == kConsumerWarps) {
-        // ---------------- producer warp: one elected lane issues the bulk copies, stage = tile % 8
-        if (lane == 0) {
+    if (warp >= kConsumerWarps) {
+        // ---------------- producer warpgroup: gives its registers away; one elected lane issues the bulk
+        // copies, stage = tile % 8
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        if (warp == kConsumerWarps && lane == 0) {
             int64_t it = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
                 const int s = (int)(it % kStages);
@@ -182,6 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) dense_scan_kernel(const DensePara
     }
 
     // ---------------- consumer warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
     // query registers: element e = 128c + 4*lane + j (zero beyond dim)
     const int slot = warp / QG;
     const int qbase = p.b0 + (warp % QG) * BQ;
@@ -323,8 +348,9 @@ struct StageRows {
 
 // queries per warp: the query registers (NCHUNK * 4 per query, x2 in float64) must not spill
 constexpr int max_bq(int nchunk, bool exact) {
-    const int budget = exact ? 6 : 12;
-    const int cap = exact ? 2 : 4;
+    const int budget = 12;     // query registers per lane: NCHUNK * 4 per query (x2 in float64)
+    const int cap = 4;         // measured on B200: 4 queries/warp x 2 warps/stage is the sweet spot at d=384
+    (void)exact;
     int bq = 1;
     while (bq * 2 <= budget / nchunk && bq * 2 <= cap) bq *= 2;
     return bq;
@@ -341,6 +367,9 @@ int dispatch_qg(int qg, const DenseParams& p, int num_sms, cudaStream_t st) {
 template <int NCHUNK, bool EXACT>
 int dispatch_bq(int bq, int qg, const DenseParams& p, int num_sms, cudaStream_t st) {
     constexpr int kMaxBQ = max_bq(NCHUNK, EXACT);
+    if constexpr (kMaxBQ >= 8) {
+        if (bq == 8) return dispatch_qg<NCHUNK, 8, EXACT>(qg, p, num_sms, st);
+    }
     if constexpr (kMaxBQ >= 4) {
         if (bq == 4) return dispatch_qg<NCHUNK, 4, EXACT>(qg, p, num_sms, st);
     }
@@ -413,6 +442,14 @@ int hs_dense_scan(const hs_index* idx, const float* queries, int32_t B, int64_t 
         while (bq > B - b0) bq >>= 1;
         int qg = 4;
         while (qg > 1 && bq * qg > B - b0) qg >>= 1;
+        if (const char* f = getenv("HS_DENSE_FORCE")) {      // tuning aid: "bq,qg"
+            int fb = 0, fq = 0;
+            if (sscanf(f, "%d,%d", &fb, &fq) == 2 && fb >= 1 && fb <= cap && fb * fq <= B - b0 &&
+                (fq == 1 || fq == 2 || fq == 4) && (fb & (fb - 1)) == 0) {
+                bq = fb;
+                qg = fq;
+            }
+        }
         p.b0 = b0;
         int rc = exact ? dispatch_chunks<true>(nchunk, bq, qg, p, idx->num_sms, (cudaStream_t)stream)
                        : dispatch_chunks<false>(nchunk, bq, qg, p, idx->num_sms, (cudaStream_t)stream);

@@ -164,7 +164,8 @@ struct FuseParams {
     const uint64_t* below;
     uint64_t* cand;       // [B, n_chunks, k]
     unsigned long long* gthr;   // [B] published lower bounds on the k-th best key (zeroed per call)
-    int64_t n, doc_base, pilot_docs;
+    uint64_t* blockmax;         // [B, kBoundBlocks] best key of each sampled block (workspace)
+    int64_t n, doc_base;
     int mode, k, n_chunks;
     float wa32, wb32;
     double wa64;
@@ -236,49 +237,144 @@ __device__ __forceinline__ float fuse_score(const FuseParams& p, const FuseConst
     return __fadd_rn(t1, t2);
 }
 
-// PILOT = true: one CTA per query scans only the first p.pilot_docs docs and publishes the k-th best key
-// of that sample as the starting bound (a subset's k-th best is a valid lower bound), so the CTAs of the
-// main launch reject almost everything with the cheap estimate and rarely need to sort.
-template <int KP, bool PILOT>
-__global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p) {
-    __shared__ Selector<KP> sel;
-    const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
-    const int64_t span = ((p.n + p.n_chunks - 1) / p.n_chunks + kThreads * kItems - 1) / (kThreads * kItems) *
-                         (kThreads * kItems);
-    const int64_t lo = PILOT ? 0 : (int64_t)chunk * span;
-    const int64_t hi = PILOT ? p.pilot_docs : ((lo + span < p.n) ? lo + span : p.n);
+// ---- starting bound from block maxima -------------------------------------------------------------
+// kBoundBlocks blocks of kBoundDocs docs are spread evenly over the shard; one warp computes the best
+// exact key of each block.  The k-th largest of those maxima is attained by k DISTINCT docs, hence it is
+// a valid lower bound on the k-th best key of the whole shard -- and for k = 100 of 1024 maxima it sits
+// around the top 0.1 % of all docs, so the main pass rejects ~99.9 % of the elements with two FMAs.
+constexpr int kBoundBlocks = 1024;
+constexpr int kBoundDocs = 128;
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const uint32_t lo = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)v, m);
+        const uint32_t hi = __shfl_xor_sync(0xFFFFFFFFu, (uint32_t)(v >> 32), m);
+        const uint64_t o = ((uint64_t)hi << 32) | lo;
+        if (o > v) v = o;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParams p) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31;
+    const int blk = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (blk >= kBoundBlocks) return;
+    const int64_t stride = (p.n / kBoundBlocks) / kBoundDocs * kBoundDocs;     // >= kBoundDocs by the host check
+    const int64_t start = (int64_t)blk * stride;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
     const float* pa = p.a + (int64_t)b * p.n;
     const float* pb = p.b ? p.b + (int64_t)b * p.n : nullptr;
+    uint64_t best = 0;
+#pragma unroll
+    for (int u = 0; u < kBoundDocs / 32; ++u) {
+        const int64_t i = start + u * 32 + lane;
+        const float a = __ldg(pa + i);
+        const float bb = pb ? __ldg(pb + i) : 0.f;
+        const uint64_t kk = hs_make_key(fuse_score(p, c, a, bb), (uint32_t)(p.doc_base + i));
+        if (kk < below && kk > best) best = kk;
+    }
+    best = warp_max_u64(best);
+    if (lane == 0) p.blockmax[(int64_t)b * kBoundBlocks + blk] = best;
+}
+
+__global__ void __launch_bounds__(kThreads) fuse_bound_kernel(const FuseParams p) {
+    __shared__ uint64_t m[kBoundBlocks];
+    const int b = blockIdx.x;
+    for (int i = threadIdx.x; i < kBoundBlocks; i += kThreads) m[i] = p.blockmax[(int64_t)b * kBoundBlocks + i];
+    __syncthreads();
+    bitonic_sort_desc<kBoundBlocks>(m);
+    // selectors drop keys <= bound, and the doc that attains m[k-1] may itself be the k-th best: publish
+    // one less (keys are unique integers).  0 if fewer than k blocks had a key: no bound.
+    if (threadIdx.x == 0) p.gthr[b] = m[p.k - 1] > 0 ? m[p.k - 1] - 1 : 0;
+}
+
+// ---- main pass ------------------------------------------------------------------------------------------
+// Optimistic streaming: with a starting bound almost nothing is appended, so the CTA first runs WITHOUT
+// any block-wide synchronisation in the loop (loads of consecutive iterations overlap freely); an append
+// that finds the candidate buffer full only raises a flag.  If the flag is up at the end the chunk is
+// redone with the synchronised selector (always correct, used from the start when there is no bound).
+template <int KP>
+__global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p) {
+    __shared__ Selector<KP> sel;
+    __shared__ int overflow;
+    constexpr int CAP = Selector<KP>::CAP;
+    const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int64_t span = ((p.n + p.n_chunks - 1) / p.n_chunks + kThreads * kItems - 1) / (kThreads * kItems) *
+                         (kThreads * kItems);
+    const int64_t lo = (int64_t)chunk * span;
+    const int64_t hi = (lo + span < p.n) ? lo + span : p.n;
+    const FuseConsts c = load_consts(p, b);
+    const uint64_t below = p.below ? p.below[b] : ~0ull;
+    const float* pa = p.a + (int64_t)b * p.n;
+    const float* pb = p.b ? p.b + (int64_t)b * p.n : nullptr;
+    unsigned long long* gthr = p.gthr + b;
+    if (tid == 0) overflow = 0;
     sel.init();
-    for (int64_t base = lo; base < hi; base += kThreads * kItems) {
-        uint64_t key[kItems];
-        float av[kItems], bv[kItems];
+    const uint64_t t0 = sel.bound(gthr);
+    bool redo = (t0 == 0);                                   // no bound: go straight to the safe path
+    if (!redo) {
+        const float thr_f = hs_dec_f32((uint32_t)(t0 >> 32));
+        for (int64_t base = lo; base < hi; base += kThreads * kItems) {
+            float av[kItems], bv[kItems];
 #pragma unroll
-        for (int j = 0; j < kItems; ++j) {
-            const int64_t i = base + j * kThreads + tid;
-            av[j] = (i < hi) ? __ldg(pa + i) : 0.f;
-            bv[j] = (pb != nullptr && i < hi) ? __ldg(pb + i) : 0.f;
-        }
-        // score the current bound stands for (bound 0 = nothing known yet -> -inf)
-        const uint64_t t = sel.bound(p.gthr + b);
-        const float thr_f = (t == 0) ? __int_as_float(0xff800000) : hs_dec_f32((uint32_t)(t >> 32));
+            for (int j = 0; j < kItems; ++j) {
+                const int64_t i = base + j * kThreads + tid;
+                av[j] = (i < hi) ? __ldg(pa + i) : 0.f;
+                bv[j] = (pb != nullptr && i < hi) ? __ldg(pb + i) : 0.f;
+            }
 #pragma unroll
-        for (int j = 0; j < kItems; ++j) {
-            const int64_t i = base + j * kThreads + tid;
-            key[j] = 0;
-            if (i < hi) {
-                if (p.mode != HS_FUSE_RAW && fuse_score_estimate(p, c, av[j], bv[j]) + c.delta < thr_f) continue;
-                const uint64_t kk = hs_make_key(fuse_score(p, c, av[j], bv[j]), (uint32_t)(p.doc_base + i));
-                if (kk < below) key[j] = kk;
+            for (int j = 0; j < kItems; ++j) {
+                const int64_t i = base + j * kThreads + tid;
+                uint64_t kk = 0;
+                if (i < hi && !(p.mode != HS_FUSE_RAW && fuse_score_estimate(p, c, av[j], bv[j]) + c.delta < thr_f)) {
+                    kk = hs_make_key(fuse_score(p, c, av[j], bv[j]), (uint32_t)(p.doc_base + i));
+                    if (kk >= below || kk <= t0) kk = 0;
+                }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, kk != 0);
+                if (m != 0) {
+                    const int leader = __ffs(m) - 1;
+                    int pos0 = 0;
+                    if (lane == leader) pos0 = atomicAdd(&sel.cnt, __popc(m));
+                    pos0 = __shfl_sync(0xFFFFFFFFu, pos0, leader);
+                    if (kk != 0) {
+                        const int pos = pos0 + __popc(m & ((1u << lane) - 1u));
+                        if (pos < CAP) sel.buf[pos] = kk;
+                        else overflow = 1;
+                    }
+                }
             }
         }
-        sel.push(key, p.k, p.gthr + b);
+        __syncthreads();
+        redo = overflow != 0;
+        if (redo) sel.init();
     }
-    if (PILOT) {
-        if (sel.cnt > KP) sel.prune(p.k, p.gthr + b);     // publishes the sample's k-th best (if it has k keys)
-        return;
+    if (redo) {
+        for (int64_t base = lo; base < hi; base += kThreads * kItems) {
+            uint64_t key[kItems];
+            float av[kItems], bv[kItems];
+#pragma unroll
+            for (int j = 0; j < kItems; ++j) {
+                const int64_t i = base + j * kThreads + tid;
+                av[j] = (i < hi) ? __ldg(pa + i) : 0.f;
+                bv[j] = (pb != nullptr && i < hi) ? __ldg(pb + i) : 0.f;
+            }
+            // score the current bound stands for (bound 0 = nothing known yet -> -inf)
+            const uint64_t t = sel.bound(gthr);
+            const float thr_f = (t == 0) ? __int_as_float(0xff800000) : hs_dec_f32((uint32_t)(t >> 32));
+#pragma unroll
+            for (int j = 0; j < kItems; ++j) {
+                const int64_t i = base + j * kThreads + tid;
+                key[j] = 0;
+                if (i < hi) {
+                    if (p.mode != HS_FUSE_RAW && fuse_score_estimate(p, c, av[j], bv[j]) + c.delta < thr_f) continue;
+                    const uint64_t kk = hs_make_key(fuse_score(p, c, av[j], bv[j]), (uint32_t)(p.doc_base + i));
+                    if (kk < below) key[j] = kk;
+                }
+            }
+            sel.push(key, p.k, gthr);
+        }
     }
     sel.finish(p.k);
     uint64_t* out = p.cand + ((int64_t)b * p.n_chunks + chunk) * p.k;
@@ -383,7 +479,7 @@ extern "C" {
 
 size_t hs_fuse_topk_workspace_bytes(int64_t n_docs, int32_t B, int32_t k) {
     if (n_docs <= 0 || B <= 0 || k <= 0) return 0;
-    return ((size_t)B * n_chunks_for(n_docs) * (size_t)k + (size_t)B) * sizeof(uint64_t);
+    return ((size_t)B * n_chunks_for(n_docs) * (size_t)k + (size_t)B + (size_t)B * kBoundBlocks) * sizeof(uint64_t);
 }
 
 int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const float* b,
@@ -415,7 +511,8 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
     p.stats = stats_enc;
     p.below = below_key;
     p.gthr = (unsigned long long*)workspace;
-    p.cand = (uint64_t*)workspace + B;
+    p.blockmax = (uint64_t*)workspace + B;
+    p.cand = (uint64_t*)workspace + B + (size_t)B * kBoundBlocks;
     HS_CUDA(cudaMemsetAsync(p.gthr, 0, (size_t)B * sizeof(uint64_t), st));
     p.n = idx->n_docs;
     p.doc_base = idx->doc_base;
@@ -426,22 +523,19 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
     p.wb32 = (float)w_b;
     p.wa64 = w_a;
     dim3 grid((unsigned)p.n_chunks, (unsigned)B);
-    // pilot pass over a small prefix when the corpus is large enough for it to pay (see the kernel)
-    p.pilot_docs = (idx->n_docs >= (int64_t)64 * 16384 && k <= 512) ? 16384 : 0;
-    if (p.pilot_docs > 0) {
-        dim3 pg(1, (unsigned)B);
-        if (k <= 128)
-            fuse_topk_kernel<128, true><<<pg, kThreads, 0, st>>>(p);
-        else
-            fuse_topk_kernel<512, true><<<pg, kThreads, 0, st>>>(p);
+    // starting bound from block maxima when the shard is large enough for it to pay (see above)
+    if (idx->n_docs >= (int64_t)kBoundBlocks * kBoundDocs * 4 && k <= kBoundBlocks / 2) {
+        dim3 bg(kBoundBlocks / (kThreads / 32), (unsigned)B);
+        fuse_blockmax_kernel<<<bg, kThreads, 0, st>>>(p);
+        fuse_bound_kernel<<<B, kThreads, 0, st>>>(p);
         HS_LAUNCH_CHECK();
     }
     if (k <= 128)
-        fuse_topk_kernel<128, false><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<128><<<grid, kThreads, 0, st>>>(p);
     else if (k <= 512)
-        fuse_topk_kernel<512, false><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<512><<<grid, kThreads, 0, st>>>(p);
     else
-        fuse_topk_kernel<2048, false><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<2048><<<grid, kThreads, 0, st>>>(p);
     HS_LAUNCH_CHECK();
     // candidate layout [B, n_chunks, k]: list stride k, query stride n_chunks * k
     return merge_dispatch(p.cand, p.n_chunks, B, k, (int64_t)k, (int64_t)p.n_chunks * k, out_keys, st);

@@ -131,7 +131,7 @@ class SearchEngine:
     def dense_launches(self, B: int, mode: Optional[str] = None) -> int:
         nchunk = (self.shard.dim + 127) // 128
         nchunk = nchunk if nchunk <= 4 else (6 if nchunk <= 6 else 8)
-        budget, cap = (6, 2) if (mode or self.dense_mode) == "exact" else (12, 4)
+        budget, cap = 12, 4
         bq = 1
         while bq * 2 <= budget // nchunk and bq * 2 <= cap:
             bq *= 2
