@@ -125,12 +125,15 @@ class Searcher:
         self.engine = SearchEngine(self.shard, dense_mode=self._dense_mode)
         self._attached = key
 
-    def _lexical_scores(self, query: str, docs: List[str]) -> np.ndarray:
-        """core.py:178-197 (rapidfuzz partial_ratio + token overlap)."""
+    def _lexical_scorer_obj(self):
         if self._lexical_scorer is None:
             from .lexical import LexicalScorer
             self._lexical_scorer = LexicalScorer(self.shard.device)
-        return self._lexical_scorer.scores(query, docs)
+        return self._lexical_scorer
+
+    def _lexical_scores(self, query: str, docs: List[str]) -> np.ndarray:
+        """core.py:178-197 (partial_ratio + token overlap), float32 [N] on the host."""
+        return self._lexical_scorer_obj().scores(query, docs)
 
     def search(self, query: str, docs_df, vectors: np.ndarray, top_k: int = 5,
                semantic_weight: Optional[float] = None, lexical_weight: Optional[float] = None,
@@ -161,7 +164,8 @@ class Searcher:
             # lex_norm * 0.0 == +0.0 for every finite lexical vector (core.py:268): skip computing it
             sc, ids = eng.search_semantic(QueryBatch(vectors=q), k, semantic_weight)
         else:
-            lex = self._lexical_scores(query, docs)
+            # device-resident lexical vector; the stored list object keys the scorer's cache
+            lex = self._lexical_scorer_obj().scores_device(query, getattr(docs_df, "contents", docs))
             sc, ids = eng.search_searcher(QueryBatch(vectors=q), lex[None, :], k, semantic_weight, lexical_weight)
         sc, ids = sc.cpu().numpy()[0], ids.cpu().numpy()[0]
         return [(float(s), docs[int(i)], doc_ids[int(i)]) for s, i in zip(sc, ids) if i >= 0]

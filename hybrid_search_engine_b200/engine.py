@@ -235,7 +235,8 @@ class SearchEngine:
 
     def search_searcher(self, qb: QueryBatch, lex: np.ndarray, k: int, sw: float, lw: float,
                         dense_mode: Optional[str] = None):
-        """Searcher.search with a lexical vector (core.py:261-271): lex float32 [B, n_docs] (host)."""
+        """Searcher.search with a lexical vector (core.py:261-271): lex float32 [B, n_docs], host array or
+        device tensor."""
         return self._run(qb, k, HS_FUSE_SEARCHER, sw, lw, True, False, dense_mode, lex=lex)
 
     def search_bm25(self, qb: QueryBatch, k: int):
@@ -257,9 +258,12 @@ class SearchEngine:
                     qt, qi, qo = self.upload_terms(qb.term_ids[s:e])
                     bm = self.bm25_score(qt, qi, qo, nb, stats)
                 if lex is not None:
-                    lx = np.ascontiguousarray(lex[s:e], dtype=np.float32)
-                    bm = self._buf("lex", lx.shape, torch.float32)
-                    bm.copy_(torch.from_numpy(lx), non_blocking=False)
+                    if isinstance(lex, torch.Tensor):
+                        bm = lex[s:e].to(self.device, torch.float32).contiguous()
+                    else:
+                        lx = np.ascontiguousarray(lex[s:e], dtype=np.float32)
+                        bm = self._buf("lex", lx.shape, torch.float32)
+                        bm.copy_(torch.from_numpy(lx), non_blocking=False)
                     check(self.lib.hs_stats_fold_minmax(ptr(bm), self.shard.n_docs, nb, 3, 2, ptr(stats),
                                                         stream_ptr(self.device)), "hs_stats_fold_minmax")
                     self.launches += 1

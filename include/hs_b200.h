@@ -137,6 +137,15 @@ size_t hs_mmr_workspace_bytes(int32_t B, int32_t C);
 int hs_mmr(const hs_index* idx, const int64_t* cand_ids, const double* rel, double lambda, int32_t B,
            int32_t C, int32_t k, void* workspace, size_t workspace_bytes, int32_t* out_sel, void* stream);
 
+/* Searcher._lexical_scores (core.py:178-197): 0.7 * partial_ratio(query, doc) / 100 + 0.3 * |Q & D| / |Q|
+ * per document (fuzzy part alone when either token set is empty), float64 arithmetic, float32 result.
+ * doc_chars / q_chars: code points of the LOWER-CASED strings; doc_tok: sorted unique token ids per doc
+ * (no stop-word removal); q_tok: sorted unique query token ids known to the vocabulary; q_set_size = |Q|.
+ * partial_ratio follows the published rapidfuzz definition (PARITY UNPINNED). */
+int hs_lexical_scores(const uint32_t* doc_chars, const int64_t* doc_off, int64_t n_docs, const uint32_t* q_chars,
+                      int32_t q_len, const int32_t* doc_tok, const int64_t* doc_tok_off, const int32_t* q_tok,
+                      int32_t n_q_tok, int32_t q_set_size, float* out, int32_t* err_flag, void* stream);
+
 /* ---- synthetic corpus generators (counter-based; hybrid_search_engine_b200/synth.py is the spec) */
 int hs_synth_embeddings(float* out, int64_t row0, int64_t n, int32_t dim, int64_t ld, uint64_t seed_key,
                         void* stream);

@@ -294,3 +294,67 @@ def test_errors_and_edge_cases(hs):
     p = hs.create_pipeline("bm25"); p.index(["", "the"])
     r = p.search("the fox", top_k=5)
     assert [x["score"] for x in r.results] == [0.0, 0.0] and [x["doc_id"] for x in r.results] == [0, 1]
+
+
+# ------------------------------------------------------------------------------------------ lexical / basic / diversity
+@pytest.mark.parametrize("name", ["t0_sample_docs", "t1_small"])
+def test_lexical_scores_and_basic_diversity_pipelines(hs, name):
+    """core.py:178-197 + basic / diversity pipelines.  rapidfuzz is PARITY UNPINNED: kernel == the shared
+    restatement bit for bit; golden values were produced by the unmodified reference running on that
+    same restatement."""
+    c = load_case(name)
+    ix = orc.build_index(c.docs, c.emb)
+    table = {orc.preprocess_text(d): e for d, e in zip(c.docs, c.emb)}
+    table.update({q: e for q, e in zip(c.queries, c.q_emb)})
+    enc = TableEncoder(table, c.emb.shape[1])
+    basic = hs.create_pipeline("basic", encoder=enc)
+    basic.index(c.docs)
+    div = hs.create_pipeline("diversity", encoder=enc)
+    div.index(c.docs)
+    for qi, q in enumerate(c.queries):
+        lex = basic.searcher._lexical_scores(q, basic.docs_df.contents)
+        assert lex.dtype == np.float32
+        assert np.array_equal(lex, c.ref[f"q{qi}_lex"]), q                      # reference (shared ratio)
+        r = basic.search(q, top_k=10)
+        ids, sc, full = orc.search_basic(ix, q, c.q_emb[qi], 10)
+        assert [x["doc_id"] for x in r.results] == ids.tolist()
+        assert [x["score"] for x in r.results] == [float(s) for s in sc]
+        assert all(type(x["score"]) is float for x in r.results)
+        assert r.metadata == {"pipeline": "basic", "weights": {"semantic": 0.7}}
+        np.testing.assert_allclose([x["score"] for x in r.results], c.ref[f"q{qi}_basic_scores"], rtol=1e-5,
+                                   atol=1e-6)                                   # unmodified reference
+        d = div.search(q, top_k=5)
+        dids, dsc = orc.search_diversity(ix, q, c.q_emb[qi], 5)
+        assert [x["doc_id"] for x in d.results] == dids.tolist()
+        assert [x["score"] for x in d.results] == [float(s) for s in dsc]
+        assert [x["diversity_rank"] for x in d.results] == list(range(len(d.results)))
+        assert d.metadata == {"pipeline": "diversity", "lambda": 0.5, "method": "mmr"}
+
+
+def test_lexical_kernel_edge_cases(hs):
+    from hybrid_search_engine_b200.lexical import LexicalScorer
+    docs = ["", "a", "the quick brown fox", "Ünïcödé straße naïve café " * 3, "x" * 700 + " needle " + "y" * 300,
+            "short", "needle", "ab" * 40, "needle in a haystack needle", "ΑΒΓ δεζ ηθι κλμ νξο πρσ τυφ χψω"]
+    sc = LexicalScorer("cuda:0")
+    queries = ["needle", "", "the the fox", "straße café", "a", "q" * 100 + " needle " + "z" * 90,
+               "ab" * 100, "δεζ needle ΑΒΓ", "w" * 300]
+    for q in queries:
+        got = sc.scores(q, docs)
+        want = orc.lexical_scores(q, docs)
+        assert np.array_equal(got, want), q
+
+
+def test_utils_mirror(hs):
+    from hybrid_search_engine_b200 import utils
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((257, 100)).astype(np.float32)
+    q = rng.standard_normal(100).astype(np.float32)
+    assert np.array_equal(utils.batch_cosine_sim(q, v), orc.cosine_exact(q, v))
+    assert utils.cosine_sim(q, v[3]) == float(orc.cosine_exact(q, v[3:4])[0])
+    assert utils.cosine_sim(np.zeros(100, np.float32), v[3]) == 0.0
+    x = rng.standard_normal(5000).astype(np.float32)
+    s, i = utils.top_k_indices(x, 17)
+    want = orc.canonical_topk(x, 17)
+    assert np.array_equal(i, want) and np.array_equal(s, x[want])
+    assert np.array_equal(utils.normalize_scores(x), orc.normalize_scores(x))
+    assert np.array_equal(utils.normalize_scores(np.full(4, 2.0, np.float32)), np.ones(4, np.float32))
