@@ -35,8 +35,13 @@ SIGNATURES = {
     "hs_stats_reset": (C.c_int, [_vp, _i32, _vp]),
     "hs_stats_decode": (C.c_int, [_vp, _vp, _i32, _vp]),
     "hs_stats_encode": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "hs_stats_to_maxform": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "hs_stats_from_maxform": (C.c_int, [_vp, _vp, _i32, _vp]),
     "hs_stats_fold_minmax": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "hs_dense_scan": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
+    "hs_index_set_dense_bf16": (C.c_int, [_vp, _vp, _i64]),
+    "hs_dense_scan_bf16_workspace_bytes": (_sz, [_vp, _i32]),
+    "hs_dense_scan_bf16": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25_workspace_bytes": (_sz, [_i64, _i32]),
     "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),

@@ -103,6 +103,25 @@ __global__ void stats_encode_kernel(const float* f, uint32_t* e, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) e[i] = hs_enc_f32(f[i]);
 }
+// all-reduce(MAX) form of the stats: (-min_a, max_a, max_b, -min_b), "nothing seen" (NaN) -> -inf
+__global__ void stats_to_maxform_kernel(const uint32_t* e, float* f, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int slot = i & 3;
+        float v = hs_dec_f32(e[i]);
+        if (slot == HS_STAT_MIN_A || slot == HS_STAT_MIN_B) v = -v;
+        f[i] = (v != v) ? __int_as_float(0xff800000) : v;
+    }
+}
+__global__ void stats_from_maxform_kernel(const float* f, uint32_t* e, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int slot = i & 3;
+        float v = f[i];
+        if (slot == HS_STAT_MIN_A || slot == HS_STAT_MIN_B) v = -v;
+        e[i] = hs_enc_f32(v);
+    }
+}
 __global__ void fold_minmax_kernel(const float* __restrict__ x, int64_t n, int slot_min, int slot_max,
                                    uint32_t* stats) {
     const int b = blockIdx.y;
@@ -153,6 +172,18 @@ int hs_stats_decode(const uint32_t* stats_enc, float* stats, int32_t B, void* st
 int hs_stats_encode(const float* stats, uint32_t* stats_enc, int32_t B, void* stream) {
     HS_REQUIRE(stats_enc != nullptr && stats != nullptr && B > 0, "hs_stats_encode: bad arguments");
     stats_encode_kernel<<<(4 * B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, stats_enc, 4 * B);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+int hs_stats_to_maxform(const uint32_t* stats_enc, float* maxform, int32_t B, void* stream) {
+    HS_REQUIRE(stats_enc != nullptr && maxform != nullptr && B > 0, "hs_stats_to_maxform: bad arguments");
+    stats_to_maxform_kernel<<<(4 * B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats_enc, maxform, 4 * B);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+int hs_stats_from_maxform(const float* maxform, uint32_t* stats_enc, int32_t B, void* stream) {
+    HS_REQUIRE(stats_enc != nullptr && maxform != nullptr && B > 0, "hs_stats_from_maxform: bad arguments");
+    stats_from_maxform_kernel<<<(4 * B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(maxform, stats_enc, 4 * B);
     HS_LAUNCH_CHECK();
     return HS_OK;
 }

@@ -1,6 +1,7 @@
 // Shared device/host helpers for the hs_b200 kernels (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -19,6 +20,11 @@ struct hs_index {
     const float* vnorm = nullptr;
     int32_t dim = 0;
     int64_t ld = 0;
+    // bf16 copy of the dense matrix for the tcgen05 GEMM path: [n_docs, ld_bf16], ld_bf16 % 64 == 0
+    const void* v_bf16 = nullptr;
+    int64_t ld_bf16 = 0;
+    CUtensorMap tmap_a;          // TMA descriptor over v_bf16: box 64 x 128, 128-byte swizzle
+    bool has_tmap_a = false;
     // csr
     const int64_t* indptr = nullptr;
     const uint2* postings = nullptr;

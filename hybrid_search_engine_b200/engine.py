@@ -123,6 +123,16 @@ class SearchEngine:
         B = q_dev.shape[0]
         cos = self._buf("cos", (B, self.shard.n_docs), torch.float32)
         m = DENSE_MODES[mode or self.dense_mode]
+        if m == _lib.HS_DENSE_BF16:
+            self.shard.ensure_bf16()
+            nbytes = self.lib.hs_dense_scan_bf16_workspace_bytes(self.shard.handle, B)
+            ws = self._buf("gemm_ws", (max(nbytes // 8, 1) + 32,), torch.int64)
+            off = (-ws.data_ptr()) % 256                           # 256-byte aligned view
+            check(self.lib.hs_dense_scan_bf16(self.shard.handle, ptr(q_dev), B, q_dev.stride(0),
+                                              ws.data_ptr() + off, nbytes, ptr(cos), ptr(stats),
+                                              stream_ptr(self.device)), "hs_dense_scan_bf16")
+            self.launches += 2 * ((B + 127) // 128)
+            return cos
         check(self.lib.hs_dense_scan(self.shard.handle, ptr(q_dev), B, q_dev.stride(0), m, ptr(cos), ptr(stats),
                                      stream_ptr(self.device)), "hs_dense_scan")
         self.launches += self.dense_launches(B, mode)
@@ -163,12 +173,13 @@ class SearchEngine:
         """C2: global (min, max) per query across shards -- one all-reduce(MAX) of B x 4 floats."""
         if self.group is None or self.world == 1:
             return stats
-        from .parallel import allreduce_stats
+        import torch.distributed as dist
         f = self._buf("stats_f", (B, 4), torch.float32)
         st = stream_ptr(self.device)
-        check(self.lib.hs_stats_decode(ptr(stats), ptr(f), B, st), "hs_stats_decode")
-        allreduce_stats(f, self.group)
-        check(self.lib.hs_stats_encode(ptr(f), ptr(stats), B, st), "hs_stats_encode")
+        # (-min, max, max, -min) form: one all-reduce(MAX); same arithmetic as parallel.allreduce_stats
+        check(self.lib.hs_stats_to_maxform(ptr(stats), ptr(f), B, st), "hs_stats_to_maxform")
+        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.group)
+        check(self.lib.hs_stats_from_maxform(ptr(f), ptr(stats), B, st), "hs_stats_from_maxform")
         self.launches += 2
         return stats
 

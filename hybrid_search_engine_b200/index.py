@@ -91,6 +91,20 @@ class DeviceIndex:
             check(self.lib.hs_index_set_dense(self.handle, ptr(self.vectors), dim, ld, ptr(self.vnorm)),
                   "hs_index_set_dense")
 
+    def ensure_bf16(self):
+        """bf16 copy of the matrix, rows padded to a multiple of 64 elements (tcgen05 GEMM path)."""
+        if getattr(self, "vectors_bf16", None) is not None:
+            return
+        if self.vectors is None:
+            raise _lib.HsError("ensure_bf16: no dense matrix")
+        ld16 = (self.dim + 63) // 64 * 64
+        v16 = torch.zeros((self.n_docs, ld16), dtype=torch.bfloat16, device=self.device)
+        step = 1 << 20
+        for s in range(0, self.n_docs, step):                   # chunked: no second float32 copy
+            v16[s:s + step, :self.dim] = self.vectors[s:s + step, :self.dim].to(torch.bfloat16)
+        self.vectors_bf16 = v16
+        check(self.lib.hs_index_set_dense_bf16(self.handle, ptr(v16), ld16), "hs_index_set_dense_bf16")
+
     # ------------------------------------------------------------------ lexical part
     def set_bm25(self, indptr: torch.Tensor, postings: torch.Tensor, dl: torch.Tensor, avgdl: float,
                  df_global: np.ndarray, n_docs_global: int, k1: float = 1.5, b: float = 0.75,

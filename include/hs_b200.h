@@ -87,6 +87,10 @@ int hs_bm25_impact_table(double avgdl, double k1, double b, uint32_t max_dl, uin
 int hs_stats_reset(uint32_t* stats_enc, int32_t B, void* stream);
 int hs_stats_decode(const uint32_t* stats_enc, float* stats, int32_t B, void* stream);
 int hs_stats_encode(const float* stats, uint32_t* stats_enc, int32_t B, void* stream);
+/* C2 bracket for doc-sharded runs: stats -> float32 [B][4] (-min_a, max_a, max_b, -min_b) so that ONE
+ * all-reduce(MAX) yields the corpus-global values (negation is exact; empty shard -> -inf), and back */
+int hs_stats_to_maxform(const uint32_t* stats_enc, float* maxform, int32_t B, void* stream);
+int hs_stats_from_maxform(const float* maxform, uint32_t* stats_enc, int32_t B, void* stream);
 /* fold min/max of x float32 [B, n] into stats slots (utils.py:67-68 for an externally produced vector,
  * e.g. the lexical scores of core.py:261); slot < 0 skips that bound */
 int hs_stats_fold_minmax(const float* x, int64_t n, int32_t B, int32_t slot_min, int32_t slot_max,
@@ -96,6 +100,14 @@ int hs_stats_fold_minmax(const float* x, int64_t n, int32_t B, int32_t slot_min,
  *     cos[b, i] float32 [B, n_docs]; folds min/max into stats slots 0/1 (utils.py:67-68) */
 int hs_dense_scan(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
                   float* cos, uint32_t* stats_enc, void* stream);
+
+/* K2b the same scan at large query batch as a bf16 tcgen05 GEMM (HS_DENSE_BF16): needs a bf16 copy of
+ *     the matrix, [n_docs, ld_bf16] with ld_bf16 a multiple of 64 (zero padded).  Norms stay float32.
+ *     Agrees with the float32 path within 1e-2; used for stage-1 retrieval at batch >= 32. */
+int hs_index_set_dense_bf16(hs_index* idx, const void* v_bf16, int64_t ld_bf16);
+size_t hs_dense_scan_bf16_workspace_bytes(const hs_index* idx, int32_t B);
+int hs_dense_scan_bf16(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, void* workspace,
+                       size_t workspace_bytes, float* cos, uint32_t* stats_enc, void* stream);
 
 /* K1  BM25.score_batch (bm25.py:83-127) for B queries over the CSR: query b owns tokens
  *     q_off[b]..q_off[b+1]-1 (known terms only, query order, duplicates kept) with their float64 idf

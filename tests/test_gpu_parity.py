@@ -358,3 +358,36 @@ def test_utils_mirror(hs):
     assert np.array_equal(i, want) and np.array_equal(s, x[want])
     assert np.array_equal(utils.normalize_scores(x), orc.normalize_scores(x))
     assert np.array_equal(utils.normalize_scores(np.full(4, 2.0, np.float32)), np.ones(4, np.float32))
+
+
+# ------------------------------------------------------------------------------------------ bf16 tcgen05 GEMM mode
+@pytest.mark.parametrize("n,d,B", [(1000, 384, 5), (20000, 384, 130), (3000, 768, 40), (777, 100, 33)])
+def test_dense_bf16_gemm_within_1e2_and_recall(hs, n, d, B):
+    """HS_DENSE_BF16 (tcgen05 GEMM): cosine within 1e-2 of the exact mode, stats consistent with the
+    produced vector, recall@100 of the semantic top-k against the exact ranking reported and >= 0.9."""
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    rng = np.random.default_rng(n + d + B)
+    v = rng.standard_normal((n, d)).astype(np.float32)
+    v[3] = 0.0
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    q[1] = 0.0
+    shard = hs.DeviceIndex("cuda:0", n)
+    shard.set_dense(torch.from_numpy(v).cuda())
+    eng = SearchEngine(shard, max_batch=256)
+    stats = eng._stats(B)
+    cos = eng.dense_scan(eng.upload_vectors(q), stats, "bf16").cpu().numpy()
+    st = stats.cpu().numpy().view(np.uint32)
+    dec = lambda e: np.array([((~e) & 0xFFFFFFFF) if not (e & 0x80000000) else (e & 0x7FFFFFFF)], np.uint32).view(np.float32)[0]
+    for b in (0, 1, B - 1):
+        want = orc.cosine_exact(q[b], v)
+        assert np.max(np.abs(cos[b] - want)) <= 1e-2
+        assert dec(int(st[b, 0])) == cos[b].min() and dec(int(st[b, 1])) == cos[b].max()
+    assert np.all(cos[1] == 0.0) and np.all(cos[:, 3] == 0.0)                  # zero query / zero row
+    k = min(100, n)
+    _, ids16 = eng.search_semantic(QueryBatch(vectors=q), k, 1.0, dense_mode="bf16")
+    ids16 = ids16.cpu().numpy().copy()
+    _, ids_ex = eng.search_semantic(QueryBatch(vectors=q), k, 1.0, dense_mode="exact")
+    ids_ex = ids_ex.cpu().numpy()
+    recall = np.mean([len(set(ids16[b]) & set(ids_ex[b])) / k for b in range(B) if b != 1])
+    print(f"bf16 recall@{k} vs exact: {recall:.4f} (n={n}, d={d}, B={B})")
+    assert recall >= 0.9
