@@ -91,8 +91,8 @@ __device__ __forceinline__ int64_t warp_lower_bound(const uint2* __restrict__ po
     const int64_t pos = lo + lane;
     const bool ge = (pos < hi) ? (__ldg(&post[pos].x) >= target) : true;
     const unsigned m = __ballot_sync(0xFFFFFFFFu, ge);
-    const int f = __ffs(m) - 1;
-    int64_t r = lo + f;
+    if (m == 0) return hi;            // exactly 32 candidates, all below the target
+    const int64_t r = lo + (__ffs(m) - 1);
     return r < hi ? r : hi;
 }
 

@@ -18,6 +18,8 @@
 // For random input the number of appended keys is O(k log(n/k)), so the pass is a pure read stream.
 // Per-CTA winners go to the workspace; a single-CTA-per-query merge kernel applies the same filter
 // to the candidate lists.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -524,7 +526,7 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
     p.wa64 = w_a;
     dim3 grid((unsigned)p.n_chunks, (unsigned)B);
     // starting bound from block maxima when the shard is large enough for it to pay (see above)
-    if (idx->n_docs >= (int64_t)kBoundBlocks * kBoundDocs * 4 && k <= kBoundBlocks / 2) {
+    if (idx->n_docs >= (int64_t)kBoundBlocks * kBoundDocs * 4 && k <= kBoundBlocks / 2 && getenv("HS_NO_BOUND") == nullptr) {
         dim3 bg(kBoundBlocks / (kThreads / 32), (unsigned)B);
         fuse_blockmax_kernel<<<bg, kThreads, 0, st>>>(p);
         fuse_bound_kernel<<<B, kThreads, 0, st>>>(p);

@@ -391,3 +391,35 @@ def test_dense_bf16_gemm_within_1e2_and_recall(hs, n, d, B):
     recall = np.mean([len(set(ids16[b]) & set(ids_ex[b])) / k for b in range(B) if b != 1])
     print(f"bf16 recall@{k} vs exact: {recall:.4f} (n={n}, d={d}, B={B})")
     assert recall >= 0.9
+
+
+def test_bm25_tile_boundary_search_regression(hs):
+    """Posting lists whose tail in a search window has exactly 32 entries below a doc-tile boundary
+    (regression: the 32-ary lower bound returned lo - 1 there) and other awkward list shapes."""
+    n = 3 * 4096 + 100
+    docs = ["pad"] * n
+    patterns = {
+        "aa": range(4096 - 32, 4096),                 # exactly 32 postings, all below the tile-1 boundary
+        "bb": range(4096 - 64, 4096),                 # 64
+        "cc": range(2 * 4096 - 33, 2 * 4096 + 1),     # straddles a boundary
+        "dd": range(0, n, 127),                       # sparse regular
+        "ee": range(4095, 4098),                      # 3 docs around a boundary
+        "ff": range(8192 - 1056, 8192),               # 1056 = 33 * 32 entries below a boundary
+        "gg": [n - 1],
+        "hh": range(0, 32),
+    }
+    docs = [[] for _ in range(n)]
+    for term, where in patterns.items():
+        for i in where:
+            docs[i].append(term)
+    docs = [" ".join(d) if d else "zz" for d in docs]
+    bm = hs.BM25()
+    bm.fit(docs)
+    st = orc.bm25_fit(docs)
+    for q in ["aa", "bb aa", "cc dd", "ee ff gg hh", "aa bb cc dd ee ff gg hh aa", "zz aa"]:
+        assert np.array_equal(bm.score_batch(q), orc.bm25_score_batch(st, q)), q
+    ids = [0, 31, 32, 4063, 4064, 4095, 4096, 8191, 8192, n - 1]
+    tids = orc.query_term_ids(st, "aa bb cc dd ee ff gg hh")
+    want = orc.bm25_score_docs(st, tids, ids)
+    for j, d in enumerate(ids):
+        assert bm.score("aa bb cc dd ee ff gg hh", d) == want[j]
