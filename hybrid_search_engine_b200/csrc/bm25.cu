@@ -49,8 +49,8 @@ struct Bm25Params {
 
 // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (dl / avgdl))), or 0 where the reference adds 0 (den <= 0):
 // float64, the reference's operation order, no contraction (bm25.py:107-110)
-__device__ __forceinline__ double bm25_frac_compute(double k1, double one_minus_b, double b, double avgdl,
-                                                    double k1p1, uint32_t tf_u, uint32_t dl) {
+__device__ __noinline__ double bm25_frac_compute(double k1, double one_minus_b, double b, double avgdl,
+                                                 double k1p1, uint32_t tf_u, uint32_t dl) {
     const double tf = (double)tf_u;
     const double kd = __dmul_rn(k1, __dadd_rn(one_minus_b, __dmul_rn(b, __ddiv_rn((double)dl, avgdl))));
     const double num = __dmul_rn(tf, k1p1);
@@ -94,6 +94,34 @@ __device__ __forceinline__ int64_t warp_lower_bound(const uint2* __restrict__ po
     if (m == 0) return hi;            // exactly 32 candidates, all below the target
     const int64_t r = lo + (__ffs(m) - 1);
     return r < hi ? r : hi;
+}
+
+// postings [lo, hi) of one token, kUnroll per thread in flight: loads, then impact gathers, then the
+// shared-memory updates (docs within one list are distinct, so the updates of a batch never collide)
+__device__ __forceinline__ void bm25_stream_slice(const Bm25Params& p, double* acc, const uint32_t* sdl, int64_t lo,
+                                                  int64_t hi, double idf, uint32_t d_lo, int tid) {
+    if (lo >= hi) return;
+    const uint2* pp = p.postings + lo;
+    const int len = (int)(hi - lo);
+    for (int i0 = tid; i0 < len; i0 += kThreads * kUnroll) {
+        uint2 pt[kUnroll];
+        double fr[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int i = i0 + u * kThreads;
+            pt[u] = (i < len) ? __ldg(pp + i) : make_uint2(0xFFFFFFFFu, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u)
+            fr[u] = (pt[u].x != 0xFFFFFFFFu) ? bm25_frac(p, pt[u].y, sdl[pt[u].x - d_lo]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (pt[u].x != 0xFFFFFFFFu) {
+                const int j = (int)(pt[u].x - d_lo);
+                acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, fr[u]));
+            }
+        }
+    }
 }
 
 // kPreTerms x kPreDepth postings per thread are fetched into registers for ALL leading tokens at once,
@@ -143,13 +171,12 @@ __global__ void __launch_bounds__(kThreads, 3) bm25_tile_kernel(const Bm25Params
         uint2 pre[kPreTerms][kPreDepth];
 #pragma unroll
         for (int t = 0; t < kPreTerms; ++t) {
+            const uint2* pp = p.postings + rng_lo[t < gn ? t : 0];
+            const int len = (t < gn) ? (int)(rng_hi[t] - rng_lo[t]) : 0;      // a slice never exceeds the tile size
 #pragma unroll
             for (int u = 0; u < kPreDepth; ++u) {
-                pre[t][u] = make_uint2(0xFFFFFFFFu, 0u);
-                if (t < gn) {
-                    const int64_t i = rng_lo[t] + tid + (int64_t)u * kThreads;
-                    if (i < rng_hi[t]) pre[t][u] = __ldg(&p.postings[i]);
-                }
+                const int i = tid + u * kThreads;
+                pre[t][u] = (i < len) ? __ldg(pp + i) : make_uint2(0xFFFFFFFFu, 0u);
             }
         }
         if (!dl_staged) {
@@ -157,52 +184,29 @@ __global__ void __launch_bounds__(kThreads, 3) bm25_tile_kernel(const Bm25Params
             dl_staged = true;
             __syncthreads();
         }
-        // ---- accumulate token by token, in query order (bm25.py:99)
-        for (int t = 0; t < gn; ++t) {
-            const double idf = s_idf[t];
-            int64_t lo = rng_lo[t];
-            const int64_t hi = rng_hi[t];
-            if (t < kPreTerms) {
+        // ---- accumulate token by token, in query order (bm25.py:99).  Leading tokens: compile-time
+        // indexed register batches first, then whatever is left of a long slice streams in batches of kUnroll.
+#pragma unroll
+        for (int t = 0; t < kPreTerms; ++t) {
+            if (t < gn) {                                           // block-uniform
+                const double idf = s_idf[t];
                 double fr[kPreDepth];
 #pragma unroll
-                for (int tt = 0; tt < kPreTerms; ++tt) {          // static register indexing
-                    if (tt == t) {
+                for (int u = 0; u < kPreDepth; ++u)
+                    fr[u] = (pre[t][u].x != 0xFFFFFFFFu) ? bm25_frac(p, pre[t][u].y, sdl[pre[t][u].x - (uint32_t)d_lo]) : 0.0;
 #pragma unroll
-                        for (int u = 0; u < kPreDepth; ++u)
-                            fr[u] = (pre[tt][u].x != 0xFFFFFFFFu)
-                                        ? bm25_frac(p, pre[tt][u].y, sdl[pre[tt][u].x - (uint32_t)d_lo]) : 0.0;
-#pragma unroll
-                        for (int u = 0; u < kPreDepth; ++u) {
-                            if (pre[tt][u].x != 0xFFFFFFFFu) {
-                                const int j = (int)(pre[tt][u].x - (uint32_t)d_lo);
-                                acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, fr[u]));
-                            }
-                        }
-                    }
-                }
-                lo += (int64_t)kThreads * kPreDepth;              // the rest of a long slice streams below
-            }
-            // batches of kUnroll postings per thread: all posting loads first, then all table gathers,
-            // then the shared-memory updates (docs within one list are distinct: no collisions)
-            for (int64_t i0 = lo + tid; i0 < hi; i0 += (int64_t)kThreads * kUnroll) {
-                uint2 pt[kUnroll];
-                double fr[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int64_t i = i0 + (int64_t)u * kThreads;
-                    pt[u] = (i < hi) ? __ldg(&p.postings[i]) : make_uint2(0xFFFFFFFFu, 0u);
-                }
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
-                    fr[u] = (pt[u].x != 0xFFFFFFFFu) ? bm25_frac(p, pt[u].y, sdl[pt[u].x - (uint32_t)d_lo]) : 0.0;
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    if (pt[u].x != 0xFFFFFFFFu) {
-                        const int j = (int)(pt[u].x - (uint32_t)d_lo);
+                for (int u = 0; u < kPreDepth; ++u) {
+                    if (pre[t][u].x != 0xFFFFFFFFu) {
+                        const int j = (int)(pre[t][u].x - (uint32_t)d_lo);
                         acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, fr[u]));
                     }
                 }
+                bm25_stream_slice(p, acc, sdl, rng_lo[t] + kThreads * kPreDepth, rng_hi[t], idf, (uint32_t)d_lo, tid);
+                __syncthreads();
             }
+        }
+        for (int t = kPreTerms; t < gn; ++t) {
+            bm25_stream_slice(p, acc, sdl, rng_lo[t], rng_hi[t], s_idf[t], (uint32_t)d_lo, tid);
             __syncthreads();
         }
     }

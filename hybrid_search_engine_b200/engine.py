@@ -289,6 +289,28 @@ class SearchEngine:
             return out_s[0], out_i[0]
         return torch.cat(out_s), torch.cat(out_i)
 
+    # ------------------------------------------------------------------ one hybrid step on device tensors
+    def hybrid_step_device(self, qd, qt, qi, qo, B: int, n_tokens: int, k: int, ws: float, wl: float,
+                           dense_mode: Optional[str] = None):
+        """The kernel chain of one hybrid_bm25 batch on device-resident inputs (no host work besides the
+        launches): stats reset, K2, K1, [C2], K3+K4, [C1 + merge], unpack.  Capturable in a CUDA graph."""
+        stats = self._stats(B)
+        cos = self.dense_scan(qd, stats, dense_mode)
+        bm = self.bm25_score(qt, qi, qo, B, stats, n_tokens)
+        stats = self._exchange_stats(stats, B)
+        keys = self.fuse_topk(HS_FUSE_HYBRID_BM25, cos, bm, stats, ws, wl, k)
+        return self.unpack(keys)
+
+    def flatten_terms(self, term_ids: Sequence[Sequence[int]]):
+        """Host side of upload_terms: (flat known term ids, their idf, offsets)."""
+        idf, df = self.shard.idf_host, self.shard.df_host
+        off, flat = [0], []
+        for ids in term_ids:
+            flat.extend(int(t) for t in ids if 0 <= int(t) < len(df) and df[int(t)] > 0)
+            off.append(len(flat))
+        arr = np.asarray(flat, dtype=np.int64)
+        return arr, (idf[arr] if len(arr) else np.zeros(0, np.float64)), np.asarray(off, dtype=np.int32)
+
     # ------------------------------------------------------------------ small kernels
     def bm25_score_docs(self, term_ids: Sequence[Sequence[int]], doc_ids: torch.Tensor) -> torch.Tensor:
         """BM25.score on candidate docs (pipelines.py:485).  doc_ids int64 [B, C] shard-local."""
