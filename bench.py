@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8, help="queries per step")
     ap.add_argument("--top-k", type=int, default=100)
     ap.add_argument("--dense-mode", default="fp32", choices=["exact", "fp32"])
-    ap.add_argument("--cpu-sample-docs", type=int, default=200_000)
+    ap.add_argument("--cpu-sample-docs", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -361,7 +361,7 @@ def run_ours(args):
                          "dense_share_of_step": dense_ms / (dev_ms / args.steps)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_run(args, steps=3, warmup=1)
+            cb = cpu_reference_run(args, steps=8, warmup=1)
             line["cpu_baseline"] = {kk: cb[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None
