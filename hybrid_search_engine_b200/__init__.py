@@ -10,7 +10,7 @@ _LAZY = {
     "create_pipeline": "pipelines", "PipelineResult": "pipelines", "BasePipeline": "pipelines",
     "BasicPipeline": "pipelines", "BM25Pipeline": "pipelines", "HybridBM25Pipeline": "pipelines",
     "MultiStagePipeline": "pipelines", "DiversityPipeline": "pipelines",
-    "Searcher": "core", "BM25": "bm25", "BM25Okapi": "bm25",
+    "Searcher": "core", "BM25": "bm25", "BM25Okapi": "bm25", "BM25Plus": "bm25",
     "extract_tokens": "extractor", "preprocess_text": "extractor", "STOPWORDS": "extractor",
     "DeviceIndex": "index", "SearchEngine": "engine", "QueryBatch": "engine",
 }

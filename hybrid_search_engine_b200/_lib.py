@@ -44,6 +44,7 @@ SIGNATURES = {
     "hs_dense_scan_bf16": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25_workspace_bytes": (_sz, [_i64, _i32]),
     "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "hs_bm25plus_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "hs_fuse_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "hs_fuse_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),

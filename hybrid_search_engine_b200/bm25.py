@@ -3,7 +3,7 @@
 ``fit`` tokenises on the host (term identity, bm25.py:58-67) and uploads a CSR inverted index;
 ``score`` / ``score_batch`` / ``search`` run the hs_b200 BM25 kernels.  ``BM25Okapi`` is the same class
 (bm25.py:145-147).  ``BM25Plus`` (bm25.py:150-179) is dense (every doc gets ``idf * delta`` per known
-query term) and is used by no pipeline; it is not part of this round's device path.
+query term) and is used by no pipeline; its ``score_batch`` runs a dedicated tile kernel.
 """
 from __future__ import annotations
 
@@ -71,8 +71,11 @@ class BM25:
         terms = [self.stats.query_term_ids(q) for q in queries]
         with torch.cuda.device(eng.device):
             qt, qi, qo = eng.upload_terms(terms)
-            sc = eng.bm25_score(qt, qi, qo, len(queries), None)
+            sc = eng.bm25_score(qt, qi, qo, len(queries), None, plus_delta=self._plus_delta())
             return sc.cpu().numpy()
+
+    def _plus_delta(self):
+        return None
 
     def score_batch(self, query: str) -> np.ndarray:
         return self.score_batch_many([query])[0]
@@ -107,3 +110,31 @@ class BM25:
 class BM25Okapi(BM25):
     """bm25.py:145-147."""
     pass
+
+
+class BM25Plus(BM25):
+    """bm25.py:150-179 -- adds ``delta`` inside the idf product, for every doc and every known query token
+    (tf = 0 included), so scores are dense.  ``score_batch`` runs the dense tile kernel; ``search`` /
+    ``score`` go through it as well (used by no pipeline in the reference)."""
+
+    def __init__(self, k1: float = 1.5, b: float = 0.75, delta: float = 1.0, **kwargs):
+        super().__init__(k1=k1, b=b, **kwargs)
+        if k1 < 0 or not 0.0 <= b <= 1.0:
+            raise ValueError("BM25Plus on the device needs k1 >= 0 and 0 <= b <= 1")
+        self.delta = delta
+
+    def _plus_delta(self):
+        return self.delta
+
+    def score(self, query: str, doc_idx: int) -> float:
+        raise NotImplementedError("BM25Plus.score for a single doc: use score_batch(query)[doc_idx] "
+                                  "(float32) -- the float64 per-doc path is only built for Okapi")
+
+    def search_many(self, queries, top_k: int = 10):
+        scores = self.score_batch_many(queries)
+        out = []
+        for row in scores:
+            k = min(int(top_k), len(row))
+            order = np.lexsort((np.arange(len(row)), -row.astype(np.float64)))[:k]
+            out.append([(int(i), float(row[i])) for i in order])
+        return out

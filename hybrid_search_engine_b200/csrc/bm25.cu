@@ -45,6 +45,7 @@ struct Bm25Params {
     uint32_t* stats;      // [B, 4] or null
     int64_t* ranges;      // [n_tokens, n_tiles + 1] posting offsets at every tile boundary (workspace)
     int n_tiles;
+    double delta;         // BM25Plus only (bm25.py:150-179)
 };
 
 // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (dl / avgdl))), or 0 where the reference adds 0 (den <= 0):
@@ -233,6 +234,69 @@ __global__ void __launch_bounds__(kThreads, 3) bm25_tile_kernel(const Bm25Params
     }
 }
 
+// BM25Plus (bm25.py:150-179): every doc receives idf * (num / den + delta) for every known query token,
+// tf = 0 included (num / den = 0 there), so the variant is dense.  Same tiling; per token the posting slice
+// is first scattered into a second float64 tile (sentinel -1 = no posting), then ALL docs of the tile are
+// updated in one ordered pass.  Requires k1 >= 0, 0 <= b <= 1 (checked on the host) so that den > 0 wherever
+// k1 > 0 and the doc is not (b == 1, dl == 0).
+__global__ void __launch_bounds__(kThreads, 2) bm25plus_tile_kernel(const Bm25Params p) {
+    extern __shared__ __align__(16) unsigned char bm25_smem[];
+    double* acc = reinterpret_cast<double*>(bm25_smem);
+    double* tmp = acc + kTileDocs;
+    uint32_t* sdl = reinterpret_cast<uint32_t*>(tmp + kTileDocs);
+    __shared__ float warp_max[kWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x, tile = blockIdx.y;
+    const int64_t d_lo = (int64_t)tile * kTileDocs;
+    const int64_t d_hi = (d_lo + kTileDocs < p.n_docs) ? d_lo + kTileDocs : p.n_docs;
+    const int ndoc = (int)(d_hi - d_lo);
+    for (int j = tid; j < ndoc; j += kThreads) {
+        acc[j] = 0.0;
+        tmp[j] = -1.0;
+        sdl[j] = p.dl[d_lo + j];
+    }
+    __syncthreads();
+    for (int t = p.q_off[b]; t < p.q_off[b + 1]; ++t) {
+        const int64_t* r = p.ranges + (int64_t)t * (p.n_tiles + 1) + tile;
+        const int64_t lo = r[0], hi = r[1];
+        const double idf = p.q_idf[t];
+        for (int64_t i = lo + tid; i < hi; i += kThreads) {
+            const uint2 pt = __ldg(&p.postings[i]);
+            const int j = (int)(pt.x - (uint32_t)d_lo);
+            tmp[j] = bm25_frac(p, pt.y, sdl[j]);
+        }
+        __syncthreads();
+        for (int j = tid; j < ndoc; j += kThreads) {
+            const double x = tmp[j];
+            if (x >= 0.0) {
+                acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, __dadd_rn(x, p.delta)));
+                tmp[j] = -1.0;
+            } else if (p.k1 > 0.0 && !(p.b == 1.0 && sdl[j] == 0)) {     // den = k1 * (...) > 0 with tf = 0
+                acc[j] = __dadd_rn(acc[j], __dmul_rn(idf, __dadd_rn(0.0, p.delta)));
+            }
+        }
+        __syncthreads();
+    }
+    float mx = 0.0f;
+    float* out = p.scores + (int64_t)b * p.n_docs + d_lo;
+    for (int j = tid; j < ndoc; j += kThreads) {
+        const float s = __double2float_rn(acc[j]);
+        out[j] = s;
+        mx = fmaxf(mx, s);
+    }
+    if (p.stats != nullptr) {
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+        if (lane == 0) warp_max[warp] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            float v = warp_max[0];
+            for (int w = 1; w < kWarps; ++w) v = fmaxf(v, warp_max[w]);
+            atomicMax(&p.stats[b * 4 + HS_STAT_MAX_B], hs_enc_f32(v));
+        }
+    }
+}
+
 // One warp per (query token, tile boundary): offset of the first posting with doc id >= boundary * kTileDocs.
 // All searches of a batch run concurrently (one ~5-round latency chain in total) instead of serially
 // at the head of every tile CTA.
@@ -316,6 +380,7 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     p.stats = nullptr;
     p.ranges = nullptr;
     p.n_tiles = (int)((idx->n_docs + kTileDocs - 1) / kTileDocs);
+    p.delta = 0.0;
     return HS_OK;
 }
 
@@ -339,9 +404,9 @@ size_t hs_bm25_workspace_bytes(int64_t n_docs, int32_t n_tokens) {
     return (size_t)n_tokens * (size_t)((n_docs + kTileDocs - 1) / kTileDocs + 1) * sizeof(int64_t);
 }
 
-int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
-                  int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
-                  uint32_t* stats_enc, void* stream) {
+static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                           int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
+                           uint32_t* stats_enc, void* stream, bool plus, double delta) {
     HS_REQUIRE(idx != nullptr, "hs_bm25_score: idx is null");
     if (idx->n_docs == 0 || B == 0) return HS_OK;
     HS_REQUIRE(B > 0 && B <= 65535 && scores != nullptr && n_tokens >= 0, "hs_bm25_score: bad arguments (B=%d)", B);
@@ -360,11 +425,34 @@ int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_i
     }
     HS_REQUIRE(p.n_tiles <= 65535, "hs_bm25_score: shard has more than 65535 doc tiles (%d)", p.n_tiles);
     dim3 grid((unsigned)B, (unsigned)p.n_tiles);
-    const size_t smem = (size_t)kTileDocs * (sizeof(double) + sizeof(uint32_t));
-    HS_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    bm25_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    if (plus) {
+        HS_REQUIRE(idx->k1 >= 0.0 && idx->b >= 0.0 && idx->b <= 1.0 && idx->avgdl > 0.0,
+                   "hs_bm25plus_score: needs k1 >= 0, 0 <= b <= 1 and a non-empty corpus");
+        p.delta = delta;
+        const size_t smem = (size_t)kTileDocs * (2 * sizeof(double) + sizeof(uint32_t));
+        HS_CUDA(cudaFuncSetAttribute(bm25plus_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bm25plus_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    } else {
+        const size_t smem = (size_t)kTileDocs * (sizeof(double) + sizeof(uint32_t));
+        HS_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bm25_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    }
     HS_LAUNCH_CHECK();
     return HS_OK;
+}
+
+int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                  int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
+                  uint32_t* stats_enc, void* stream) {
+    return bm25_score_impl(idx, q_terms, q_idf, q_off, B, n_tokens, workspace, workspace_bytes, scores, stats_enc, stream,
+                           false, 0.0);
+}
+
+int hs_bm25plus_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                      int32_t B, int32_t n_tokens, double delta, void* workspace, size_t workspace_bytes,
+                      float* scores, uint32_t* stats_enc, void* stream) {
+    return bm25_score_impl(idx, q_terms, q_idf, q_off, B, n_tokens, workspace, workspace_bytes, scores, stats_enc, stream,
+                           true, delta);
 }
 
 int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,

@@ -158,14 +158,19 @@ class SearchEngine:
         return n
 
     def bm25_score(self, q_terms, q_idf, q_off, B: int, stats: Optional[torch.Tensor],
-                   n_tokens: Optional[int] = None) -> torch.Tensor:
+                   n_tokens: Optional[int] = None, plus_delta: Optional[float] = None) -> torch.Tensor:
         n_tokens = self._n_tokens if n_tokens is None else int(n_tokens)
         sc = self._buf("bm25", (B, self.shard.n_docs), torch.float32)
         nbytes = self.lib.hs_bm25_workspace_bytes(self.shard.n_docs, n_tokens)
         ws = self._buf("bm25_ws", (max(nbytes // 8, 1),), torch.int64)
-        check(self.lib.hs_bm25_score(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, n_tokens,
-                                     ptr(ws), nbytes, ptr(sc), ptr(stats), stream_ptr(self.device)),
-              "hs_bm25_score")
+        if plus_delta is not None:
+            check(self.lib.hs_bm25plus_score(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, n_tokens,
+                                             float(plus_delta), ptr(ws), nbytes, ptr(sc), ptr(stats),
+                                             stream_ptr(self.device)), "hs_bm25plus_score")
+        else:
+            check(self.lib.hs_bm25_score(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, n_tokens,
+                                         ptr(ws), nbytes, ptr(sc), ptr(stats), stream_ptr(self.device)),
+                  "hs_bm25_score")
         self.launches += 2 if n_tokens > 0 else 1
         return sc
 

@@ -116,6 +116,7 @@ class DeviceIndex:
         self.n_terms = self.indptr.numel() - 1
         self.avgdl, self.k1, self.b = avgdl, float(k1), float(b)
         self.df_host = np.asarray(df_global, dtype=np.int64)
+        self.n_docs_global = int(n_docs_global)
         self.idf_host = idf_from_df(n_docs_global, self.df_host)
         if max_dl is None:
             max_dl = int(self.dl.max().item()) if self.n_docs else 0
@@ -135,6 +136,31 @@ class DeviceIndex:
             check(self.lib.hs_index_set_doc_stats(self.handle, ptr(self.dl), float(avgdl), self.k1, self.b,
                                                   ptr(self.impact_table), self.max_dl, self.tf_cap),
                   "hs_index_set_doc_stats")
+
+    # ------------------------------------------------------------------ persistence (checkpoint / resume)
+    def save(self, path: str):
+        """Serialise the shard (dense matrix, CSR, doc stats, global df) so that ``index()`` need not be
+        repeated -- the reference re-embeds and re-fits on every start (api.py:130-137, cli.py:28-33)."""
+        state = {"format": "hs_b200_shard_v1", "n_docs": self.n_docs, "doc_base": self.doc_base, "dim": self.dim}
+        if self.vectors is not None:
+            state["vectors"] = self.vectors[:, :self.dim].cpu()
+        if self.indptr is not None:
+            state.update(indptr=self.indptr.cpu(), postings=self.postings.cpu(), dl=self.dl.cpu(), avgdl=self.avgdl,
+                         k1=self.k1, b=self.b, df=self.df_host, n_docs_global=self.n_docs_global, max_dl=self.max_dl)
+        torch.save(state, path)
+
+    @classmethod
+    def load(cls, path: str, device) -> "DeviceIndex":
+        state = torch.load(path, map_location="cpu", weights_only=False)
+        if state.get("format") != "hs_b200_shard_v1":
+            raise ValueError(f"{path}: not an hs_b200 shard file")
+        shard = cls(device, state["n_docs"], state["doc_base"])
+        if "vectors" in state:
+            shard.set_dense(state["vectors"].to(shard.device))
+        if "indptr" in state:
+            shard.set_bm25(state["indptr"], state["postings"], state["dl"], state["avgdl"], state["df"],
+                           state["n_docs_global"], state["k1"], state["b"], max_dl=state["max_dl"])
+        return shard
 
     @property
     def has_dense(self) -> bool:

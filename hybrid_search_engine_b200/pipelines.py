@@ -10,7 +10,7 @@ MiniLM inside Indexer/Searcher, indexer.py:91, core.py:134):
 
 * ``encoder=``      object with ``encode(list[str]) -> float32 [n, d]`` (defaults to
                     sentence-transformers ``all-MiniLM-L6-v2`` if installed, else a clear error)
-* ``device=``       CUDA device of the shard, ``dense_mode=`` "exact" | "fp32"
+* ``device=``       CUDA device of the shard, ``dense_mode=`` "exact" | "fp32" | "bf16" (tcgen05 GEMM)
 * ``index(documents, source_paths=None, embeddings=None)``  precomputed document vectors
 * ``search(query, top_k, query_vector=None)``               precomputed query vector
 * ``search_many(queries, top_k, query_vectors=None)``       one batched launch chain for B queries
@@ -115,6 +115,13 @@ class BasicPipeline(BasePipeline):
             results=[{"score": s, "content": c, "doc_id": d} for s, c, d in results],
             metadata={"pipeline": "basic", "weights": {"semantic": self.semantic_weight}},
             highlighted=None)
+
+
+    def search_many(self, queries: Sequence[str], top_k: int = 5, *, query_vectors=None) -> List[PipelineResult]:
+        """One result per query (the lexical scorer is per query, the dense scan is shared by the batch
+        only through the device-resident index)."""
+        qv = self._query_vectors(queries, query_vectors)
+        return [self.search(q, top_k, query_vector=qv[i]) for i, q in enumerate(queries)]
 
 
 # ------------------------------------------------------------------------------------------ bm25
@@ -238,19 +245,27 @@ class MultiStagePipeline(BasePipeline):
         return out
 
     def search(self, query: str, top_k: int = None, *, query_vector=None) -> PipelineResult:
-        top_k = top_k or self.final_k
         qv = None if query_vector is None else np.asarray(query_vector, np.float32)[None, :]
-        stage2 = self.stages_1_2([query], query_vectors=qv)[0]
+        return self.search_many([query], top_k, query_vectors=qv)[0]
+
+    def search_many(self, queries: Sequence[str], top_k: int = None, *, query_vectors=None) -> List[PipelineResult]:
+        """Stages 1-2 for the whole batch in one launch chain (set ``dense_mode="bf16"`` on the pipeline for the
+        tcgen05 GEMM at large batch), stage 3 per query through the reranker hook."""
+        top_k = top_k or self.final_k
+        stage2 = self.stages_1_2(queries, query_vectors=query_vectors)
         if self._reranker is None:
             from .core import CrossEncoderReranker      # stage 3 is transformer inference: external hook
             self._reranker = CrossEncoderReranker()
-        final = self._reranker.rerank(query, stage2, top_k=top_k)
-        return PipelineResult(
-            query=query,
-            results=[{"score": s, "content": c, "doc_id": d, "stage": "final"} for s, c, d in final],
-            metadata={"pipeline": "multi_stage", "stage1_k": self.stage1_k, "stage2_k": self.stage2_k,
-                      "final_k": top_k},
-            highlighted=None)
+        out = []
+        for q, cand in zip(queries, stage2):
+            final = self._reranker.rerank(q, cand, top_k=top_k)
+            out.append(PipelineResult(
+                query=q,
+                results=[{"score": s, "content": c, "doc_id": d, "stage": "final"} for s, c, d in final],
+                metadata={"pipeline": "multi_stage", "stage1_k": self.stage1_k, "stage2_k": self.stage2_k,
+                          "final_k": top_k},
+                highlighted=None))
+        return out
 
 
 # ------------------------------------------------------------------------------------------ diversity
@@ -293,6 +308,10 @@ class DiversityPipeline(BasePipeline):
             results=[{"score": results[i][0], "content": results[i][1], "doc_id": results[i][2],
                       "diversity_rank": rank} for rank, i in enumerate(selected)],
             metadata={"pipeline": "diversity", "lambda": self.lambda_param, "method": "mmr"})
+
+    def search_many(self, queries: Sequence[str], top_k: int = 5, *, query_vectors=None) -> List[PipelineResult]:
+        qv = self._query_vectors(queries, query_vectors)
+        return [self.search(q, top_k, query_vector=qv[i]) for i, q in enumerate(queries)]
 
 
 # ------------------------------------------------------------------------------------------ factory

@@ -119,6 +119,12 @@ int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_i
                   int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
                   uint32_t* stats_enc, void* stream);
 
+/* BM25Plus.score over all docs (bm25.py:150-179): idf * (num / den + delta) for EVERY doc and known query
+ * token (dense variant, used by no pipeline); same arguments as hs_bm25_score plus delta */
+int hs_bm25plus_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                      int32_t B, int32_t n_tokens, double delta, void* workspace, size_t workspace_bytes,
+                      float* scores, uint32_t* stats_enc, void* stream);
+
 /* BM25.score (bm25.py:83-112) for selected docs only: multi_stage stage 2 (pipelines.py:485).
  * doc_ids int64 [B, C] (shard-local, < 0 = padding), out float64 [B, C], unrounded */
 int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf,

@@ -173,5 +173,26 @@ def main():
         print(name, "done", {k: v.shape for k, v in list(g.items())[:4]})
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def main_plus():
+    """BM25Plus (bm25.py:150-179) on the t1_small corpus -> tests/golden/t1_small_bm25plus.npz."""
+    ref = refload.load()
+    spec = synth.SynthSpec(n_docs=400, vocab=300, dim=48, min_len=3, max_len=30)
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    docs, _ = t1_corpus(spec, th)
+    queries, _ = t1_extra_queries(spec, synth.query_texts(spec, 0, 6, th))
+    out = {}
+    for name, kw in (("d1", dict(delta=1.0)), ("d05_k12", dict(k1=1.2, b=0.5, delta=0.5))):
+        bm = ref.bm25.BM25Plus(**kw)
+        bm.fit(docs)
+        for qi, q in enumerate(queries):
+            out[f"{name}_q{qi}"] = bm.score_batch(q)
+    np.savez_compressed(os.path.join(GOLDEN, "t1_small_bm25plus.npz"), **out)
+    print("bm25plus golden written", len(out))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "plus":
+    main_plus()

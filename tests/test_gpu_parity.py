@@ -423,3 +423,38 @@ def test_bm25_tile_boundary_search_regression(hs):
     want = orc.bm25_score_docs(st, tids, ids)
     for j, d in enumerate(ids):
         assert bm.score("aa bb cc dd ee ff gg hh", d) == want[j]
+
+
+def test_bm25plus_bit_identical_to_reference(hs):
+    """BM25Plus (bm25.py:150-179): dense variant, float64 ordered accumulation, float32 rounding."""
+    import os
+    c = load_case("t1_small")
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "t1_small_bm25plus.npz")))
+    for name, kw in (("d1", dict(delta=1.0)), ("d05_k12", dict(k1=1.2, b=0.5, delta=0.5))):
+        bm = hs.BM25Plus(**kw)
+        bm.fit(c.docs)
+        got = bm.score_batch_many(c.queries)
+        for qi, q in enumerate(c.queries):
+            assert np.array_equal(got[qi], g[f"{name}_q{qi}"]), (name, q)        # unmodified reference
+        top = bm.search(c.queries[0], top_k=5)
+        want = orc.canonical_topk(g[f"{name}_q0"], 5)
+        assert [i for i, _ in top] == want.tolist()
+
+
+def test_shard_save_load_roundtrip(hs, tmp_path):
+    c = load_case("t1_small")
+    table = {orc.preprocess_text(d): e for d, e in zip(c.docs, c.emb)}
+    table.update({q: e for q, e in zip(c.queries, c.q_emb)})
+    p = hs.create_pipeline("hybrid_bm25", encoder=TableEncoder(table, c.emb.shape[1]))
+    p.index(c.docs)
+    want = p.search_many(c.queries[:4], top_k=20)
+    path = str(tmp_path / "shard.pt")
+    p.searcher.shard.save(path)
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    shard = hs.DeviceIndex.load(path, "cuda:0")
+    eng = SearchEngine(shard)
+    qb = QueryBatch(vectors=c.q_emb[:4], term_ids=[p.bm25.stats.query_term_ids(q) for q in c.queries[:4]])
+    sc, ids = eng.search_hybrid_bm25(qb, 20, 0.6, 0.4)
+    for qi in range(4):
+        assert ids[qi].cpu().tolist() == [r["doc_id"] for r in want[qi].results]
+        assert np.array_equal(sc[qi].cpu().numpy(), np.array([r["score"] for r in want[qi].results], np.float32))

@@ -11,6 +11,7 @@ from oracle import hybrid_oracle as orc
 from tests.golden_cases import load_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE_INDEX_FAISS_SHA256 = "e081a6078b5cac6b2488a55c80a8af4029d0adc35c73edfadd94eb3e1edc39ca"
 
 
 def test_library_exports_every_declared_symbol():
@@ -111,3 +112,22 @@ def test_synth_is_deterministic_and_well_formed():
     # streams of different seeds do not alias (the bug class the seed scrambling prevents)
     assert synth.query_texts(spec, 0, 8) != synth.doc_texts(spec, 0, 8)
     assert not np.array_equal(synth.query_embeddings(spec, 0, 8), synth.embeddings(spec, 0, 8))
+
+
+def test_faiss_flat_io_reproduces_the_reference_file(tmp_path):
+    """The writer must emit the reference's index.faiss byte for byte from its 12 rows (sha256 of the file
+    at /root/reference/index.faiss, recorded when the golden fixtures were made)."""
+    import hashlib
+    from hybrid_search_engine_b200 import faiss_io
+    c = load_case("t0_sample_docs")
+    path = str(tmp_path / "index.faiss")
+    faiss_io.write_index_flat(path, c.emb, metric=0)
+    assert hashlib.sha256(open(path, "rb").read()).hexdigest() == REFERENCE_INDEX_FAISS_SHA256
+    vec, metric = faiss_io.read_index_flat(path)
+    assert metric == 0 and vec.shape == (12, 384) and np.array_equal(vec, c.emb)
+    faiss_io.write_index_flat(path, c.emb * 3.0, metric=0, normalize=True)      # FAISSIndex.add normalises
+    vec, _ = faiss_io.read_index_flat(path)
+    assert np.allclose(np.linalg.norm(vec, axis=1), 1.0, atol=1e-6)
+    with pytest.raises(ValueError):
+        open(path, "wb").write(b"nope" + b"\\0" * 60)
+        faiss_io.read_index_flat(path)
