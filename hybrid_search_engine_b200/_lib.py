@@ -49,6 +49,7 @@ SIGNATURES = {
     "hs_fuse_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "hs_fuse_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),
     "hs_topk_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "hs_scatter_keys": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _vp, _vp]),
     "hs_keys_unpack": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     "hs_mmr_workspace_bytes": (_sz, [_i32, _i32]),
     "hs_mmr": (C.c_int, [_vp, _vp, _vp, _f64, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),

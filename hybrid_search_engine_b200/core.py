@@ -93,11 +93,15 @@ class Searcher:
     def __init__(self, model_name: str = "all-MiniLM-L6-v2", db_path: str = "index.duckdb", use_faiss: bool = False,
                  faiss_index_path: str = "index.faiss", enable_query_memory: bool = True, *, encoder=None,
                  device=None, dense_mode: str = "exact", lexical_scorer=None):
-        if use_faiss:
-            raise NotImplementedError("use_faiss=True (core.py:159-168) is not on the pipeline path")
+        # use_faiss=True (core.py:148-168): the rows of `faiss_index_path` (a FAISS IndexFlatIP file,
+        # L2-normalised at add time) replace `vectors`; only the top min(2k, N) inner products keep their
+        # score.  Not reachable from the pipelines (they construct Searcher(db_path=...)).  PARITY UNPINNED:
+        # faiss is not installable here; cosine of the stored rows stands in for its sgemm inner product.
         self.model = encoder
         self.db_path = db_path
-        self.use_faiss = False
+        self.use_faiss = bool(use_faiss)
+        self.faiss_index_path = faiss_index_path
+        self._faiss_rows = None
         self.query_memory = None
         self._device = device
         self._dense_mode = dense_mode
@@ -144,7 +148,13 @@ class Searcher:
         lexical_weight = lexical_weight if lexical_weight is not None else 0.3
         if not np.isclose(semantic_weight + lexical_weight, 1.0):
             raise ValueError("semantic_weight and lexical_weight must sum to 1.0")
-        self.attach(docs_df, vectors)
+        if self.use_faiss and self._faiss_rows is None:
+            import os
+            if os.path.exists(self.faiss_index_path):          # core.py:148-157: silently brute-force otherwise
+                from .faiss_io import read_index_flat
+                self._faiss_rows, _ = read_index_flat(self.faiss_index_path)
+        use_faiss = self.use_faiss and self._faiss_rows is not None
+        self.attach(docs_df, self._faiss_rows if use_faiss else vectors)
         docs = docs_df["content"].to_list()
         doc_ids = docs_df["doc_id"].to_list()
         n = len(docs)
@@ -160,7 +170,12 @@ class Searcher:
         if k == 0:
             return []
         eng = self.engine
-        if lexical_weight == 0.0:
+        if use_faiss:
+            lex = None
+            if lexical_weight != 0.0:
+                lex = self._lexical_scorer_obj().scores_device(query, getattr(docs_df, "contents", docs))[None, :]
+            sc, ids = eng.search_faiss_style(QueryBatch(vectors=q), lex, k, semantic_weight, lexical_weight)
+        elif lexical_weight == 0.0:
             # lex_norm * 0.0 == +0.0 for every finite lexical vector (core.py:268): skip computing it
             sc, ids = eng.search_semantic(QueryBatch(vectors=q), k, semantic_weight)
         else:

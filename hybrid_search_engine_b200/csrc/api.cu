@@ -155,7 +155,31 @@ __global__ void keys_unpack_kernel(const uint64_t* keys, int64_t n, float* score
     }
 }
 
+// out[b, :] = 0 except out[b, id - doc_base] = score for every non-empty key (FAISS-style sparse scores)
+__global__ void scatter_keys_kernel(const uint64_t* keys, int64_t count, int k, int64_t n, int64_t doc_base, float* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        const uint64_t key = keys[i];
+        if (key != 0) {
+            const int64_t id = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu)) - doc_base;
+            if (id >= 0 && id < n) out[(i / k) * n + id] = hs_dec_f32((uint32_t)(key >> 32));
+        }
+    }
+}
+
 extern "C" {
+
+int hs_scatter_keys(const uint64_t* keys, int32_t B, int32_t k, int64_t n_docs, int64_t doc_base, float* out,
+                    void* stream) {
+    HS_REQUIRE(keys != nullptr && out != nullptr && B > 0 && k > 0 && n_docs >= 0, "hs_scatter_keys: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_docs == 0) return HS_OK;
+    HS_CUDA(cudaMemsetAsync(out, 0, (size_t)B * n_docs * sizeof(float), st));
+    const int64_t count = (int64_t)B * k;
+    scatter_keys_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(keys, count, k, n_docs, doc_base, out);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
 
 int hs_stats_reset(uint32_t* stats_enc, int32_t B, void* stream) {
     HS_REQUIRE(stats_enc != nullptr && B > 0, "hs_stats_reset: bad arguments");

@@ -255,6 +255,34 @@ class SearchEngine:
         device tensor."""
         return self._run(qb, k, HS_FUSE_SEARCHER, sw, lw, True, False, dense_mode, lex=lex)
 
+    def search_faiss_style(self, qb: QueryBatch, lex, k: int, sw: float, lw: float, dense_mode: Optional[str] = None):
+        """Searcher.search with use_faiss=True (core.py:244-250,264-271): only the best min(2k, N) cosine scores
+        survive, every other doc gets semantic score 0.0 BEFORE the min-max normalisation.  Single shard."""
+        if self.world > 1:
+            raise NotImplementedError("faiss-style retrieval is not sharded")
+        B, n = len(qb), self.shard.n_docs
+        k2 = min(2 * int(k), n)
+        with torch.cuda.device(self.device):
+            stats0 = self._stats(B)
+            cos = self.dense_scan(self.upload_vectors(qb.vectors), stats0, dense_mode)
+            keys = self._select(HS_FUSE_RAW, cos, None, None, 1.0, 0.0, k2).clone()
+            sparse = self._buf("sparse_sem", (B, n), torch.float32)
+            check(self.lib.hs_scatter_keys(ptr(keys), B, k2, n, self.shard.doc_base, ptr(sparse),
+                                           stream_ptr(self.device)), "hs_scatter_keys")
+            stats = self._stats(B)
+            check(self.lib.hs_stats_fold_minmax(ptr(sparse), n, B, 0, 1, ptr(stats), stream_ptr(self.device)),
+                  "hs_stats_fold_minmax")
+            self.launches += 3
+            bm = None
+            if lex is not None:
+                bm = lex.to(self.device, torch.float32).contiguous() if isinstance(lex, torch.Tensor) else \
+                    torch.from_numpy(np.ascontiguousarray(lex, dtype=np.float32)).to(self.device)
+                check(self.lib.hs_stats_fold_minmax(ptr(bm), n, B, 3, 2, ptr(stats), stream_ptr(self.device)),
+                      "hs_stats_fold_minmax")
+                self.launches += 1
+            out = self._select(HS_FUSE_SEARCHER, sparse, bm, stats, sw, lw if bm is not None else 0.0, k)
+            return self.unpack(out)
+
     def search_bm25(self, qb: QueryBatch, k: int):
         """BM25.search (bm25.py:129-142): raw float32 BM25 score, canonical tie order."""
         return self._run(qb, k, HS_FUSE_RAW, 1.0, 0.0, False, True, None)

@@ -145,6 +145,10 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
 /* C1 merge: keys uint64 [n_lists, B, k] (e.g. the all-gathered per-shard lists) -> out_keys [B, k] */
 int hs_topk_merge(const uint64_t* keys, int32_t n_lists, int32_t B, int32_t k, uint64_t* out_keys,
                   void* stream);
+/* Searcher._semantic_search_faiss bookkeeping (core.py:244-250): scores of the docs named by keys [B, k]
+ * scattered into a zeroed float32 [B, n_docs] vector (every other doc keeps 0.0) */
+int hs_scatter_keys(const uint64_t* keys, int32_t B, int32_t k, int64_t n_docs, int64_t doc_base, float* out,
+                    void* stream);
 /* keys -> (float32 score, int64 global doc id; -1 where key == 0) */
 int hs_keys_unpack(const uint64_t* keys, int64_t count, float* scores, int64_t* doc_ids, void* stream);
 

@@ -454,3 +454,20 @@ def search_diversity(ix: OracleIndex, query: str, q_vec: np.ndarray, top_k: int,
     rel = diversity_relevance([float(x) for x in sc])
     sel = mmr_select(ix.vectors[cand], rel, lam, top_k, ix.vnorm[cand])
     return cand[sel], sc[sel]
+
+
+def search_faiss_style(ix: OracleIndex, query: str, q_vec: np.ndarray, top_k: int, sw: float = 0.7,
+                       ratio_fn=partial_ratio):
+    """core.py:244-250 + 264-276 with use_faiss=True (PARITY UNPINNED: faiss is not installable; the inner
+    product of the stored L2-normalised rows with the normalised query is restated as the conformance cosine).
+    Only the best min(2k, N) semantic scores survive, all other docs keep 0.0 before min-max."""
+    n = len(ix.vectors)
+    cos = cosine_exact(q_vec, ix.vectors, ix.vnorm)
+    keep = canonical_topk(cos, min(2 * top_k, n))
+    sem = np.zeros(n, np.float32)
+    sem[keep] = cos[keep]
+    lw = 1.0 - sw
+    lex = lexical_scores(query, ix.contents, ratio_fn) if lw != 0.0 else np.zeros(n, np.float32)
+    hyb = searcher_hybrid(sem, lex, sw, lw)
+    ids = canonical_topk(hyb, top_k)
+    return ids, hyb[ids]

@@ -458,3 +458,23 @@ def test_shard_save_load_roundtrip(hs, tmp_path):
     for qi in range(4):
         assert ids[qi].cpu().tolist() == [r["doc_id"] for r in want[qi].results]
         assert np.array_equal(sc[qi].cpu().numpy(), np.array([r["score"] for r in want[qi].results], np.float32))
+
+
+def test_searcher_use_faiss_semantics(hs, tmp_path):
+    """Searcher(use_faiss=True) (core.py:148-168,244-250): rows come from the IndexFlatIP file, only the top
+    min(2k, N) semantic scores survive.  Parity unpinned against faiss itself; checked against the oracle."""
+    from hybrid_search_engine_b200 import faiss_io
+    from hybrid_search_engine_b200.core import DocTable
+    c = load_case("t0_sample_docs")
+    path = str(tmp_path / "index.faiss")
+    faiss_io.write_index_flat(path, c.emb, metric=0, normalize=True)
+    rows, _ = faiss_io.read_index_flat(path)
+    ix = orc.build_index(c.docs, rows)
+    s = hs.Searcher(use_faiss=True, faiss_index_path=path)
+    table = DocTable([orc.preprocess_text(d) for d in c.docs])
+    for qi, q in enumerate(c.queries):
+        for k in (2, 5):
+            got = s.search(q, table, c.emb, top_k=k, query_vector=c.q_emb[qi])
+            ids, sc = orc.search_faiss_style(ix, q, c.q_emb[qi], k)
+            assert [d for _, _, d in got] == ids.tolist(), (q, k)
+            assert [x for x, _, _ in got] == [float(v) for v in sc]
