@@ -54,6 +54,8 @@ SIGNATURES = {
     "hs_mmr_workspace_bytes": (_sz, [_i32, _i32]),
     "hs_mmr": (C.c_int, [_vp, _vp, _vp, _f64, _i32, _i32, _i32, _vp, _sz, _vp, _vp]),
     "hs_lexical_scores": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "hs_token_flags": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "hs_token_hashes": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
     "hs_synth_embeddings": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _u64, _vp]),
     "hs_synth_doc_lengths": (C.c_int, [_vp, _i64, _i64, _u64, _u32, _u32, _vp]),
     "hs_synth_token_keys": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _u64, _vp, _i32, _vp]),

@@ -18,11 +18,18 @@ from .index import DeviceIndex, LexicalStats
 
 
 class BM25:
-    def __init__(self, k1: float = 1.5, b: float = 0.75, remove_stopwords: bool = True, *, device=None):
+    def __init__(self, k1: float = 1.5, b: float = 0.75, remove_stopwords: bool = True, *, device=None,
+                 index_build: str = "host"):
+        """``index_build`` (extension): "host" keeps the vocabulary strings (``doc_freqs`` / ``idf`` dicts as in
+        the reference); "device" tokenises and builds the CSR on the GPU (index_build.py) and keeps only term
+        hashes -- same scores, ~100x faster ``fit`` on large corpora."""
+        if index_build not in ("host", "device"):
+            raise ValueError(f"index_build must be 'host' or 'device', got {index_build!r}")
         self.k1 = k1
         self.b = b
         self.remove_stopwords = remove_stopwords
         self._device = device
+        self.index_build = index_build
         self.stats = LexicalStats(remove_stopwords)
         self.shard: Optional[DeviceIndex] = None
         self.engine: Optional[SearchEngine] = None
@@ -31,18 +38,26 @@ class BM25:
         self.doc_lengths: List[int] = []
 
     # ---- corpus statistics in the reference's shapes (built lazily, host side) -----------------
+    def _vocab(self) -> Dict[str, int]:
+        v = getattr(self.stats, "vocab", None)
+        if v is None:
+            raise _lib.HsError("the device index build keeps term hashes, not strings; use index_build='host'")
+        return v
+
     @property
     def doc_freqs(self) -> Dict[str, int]:
-        return {t: int(self.stats.df[i]) for t, i in self.stats.vocab.items()}
+        return {t: int(self.stats.df[i]) for t, i in self._vocab().items()}
 
     @property
     def idf(self) -> Dict[str, float]:
         if self.shard is None or self.shard.idf_host is None:
             return {}
-        return {t: float(self.shard.idf_host[i]) for t, i in self.stats.vocab.items()}
+        return {t: float(self.shard.idf_host[i]) for t, i in self._vocab().items()}
 
     def fit(self, documents: Sequence[str], *, shard: Optional[DeviceIndex] = None):
         """bm25.py:45-81.  ``shard``: attach to an existing device shard (the pipeline's dense one)."""
+        if self.index_build == "device":
+            return self._fit_device(documents, shard)
         st = self.stats = LexicalStats(self.remove_stopwords).fit(documents)
         self.doc_count = st.doc_count
         self.avg_doc_len = st.avg_doc_len
@@ -60,6 +75,29 @@ class BM25:
         shard.set_bm25(torch.from_numpy(st.indptr), torch.from_numpy(st.postings.view(np.int32)),
                        torch.from_numpy(st.doc_lengths.astype(np.uint32).view(np.int32)), float(st.avg_doc_len),
                        st.df, st.doc_count, self.k1, self.b)
+        self.engine = SearchEngine(shard)
+
+    def _fit_device(self, documents: Sequence[str], shard: Optional[DeviceIndex]):
+        from .index_build import DeviceLexicalStats
+        if not torch.cuda.is_available():
+            raise _lib.HsError("no CUDA device: the device index build has no CPU fallback")
+        if len(documents) == 0:
+            self.stats = LexicalStats(self.remove_stopwords).fit(documents)
+            self.doc_count, self.avg_doc_len, self.doc_lengths = 0, 0, []
+            self.shard = self.engine = None
+            return
+        dev = shard.device if shard is not None else (
+            torch.device(self._device) if self._device is not None else
+            torch.device("cuda", torch.cuda.current_device()))
+        st = self.stats = DeviceLexicalStats(dev, self.remove_stopwords).fit(documents)
+        self.doc_count = st.doc_count
+        self.avg_doc_len = st.avg_doc_len
+        self.doc_lengths = st.doc_lengths.cpu().tolist()
+        if shard is None:
+            shard = DeviceIndex(dev, st.doc_count)
+        self.shard = shard
+        shard.set_bm25(st.indptr, st.postings, st.doc_lengths, float(st.avg_doc_len), st.df, st.doc_count,
+                       self.k1, self.b, max_dl=st.max_dl)
         self.engine = SearchEngine(shard)
 
     # ---- scoring --------------------------------------------------------------------------------

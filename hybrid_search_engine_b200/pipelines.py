@@ -10,6 +10,7 @@ MiniLM inside Indexer/Searcher, indexer.py:91, core.py:134):
 
 * ``encoder=``      object with ``encode(list[str]) -> float32 [n, d]`` (defaults to
                     sentence-transformers ``all-MiniLM-L6-v2`` if installed, else a clear error)
+* ``index_build=``  "host" | "device": where ``BM25.fit`` tokenises and builds the CSR (index_build.py)
 * ``device=``       CUDA device of the shard, ``dense_mode=`` "exact" | "fp32" | "bf16" (tcgen05 GEMM)
 * ``index(documents, source_paths=None, embeddings=None)``  precomputed document vectors
 * ``search(query, top_k, query_vector=None)``               precomputed query vector
@@ -44,7 +45,7 @@ class BasePipeline:
     """pipelines.py:33-59.  Highlighting is outside the hot path."""
 
     def __init__(self, db_path: str = "index.duckdb", enable_highlighting: bool = False, *,
-                 encoder=None, device=None, dense_mode: str = "exact"):
+                 encoder=None, device=None, dense_mode: str = "exact", index_build: str = "host"):
         if enable_highlighting:
             raise NotImplementedError("highlighting is outside the B200 hot path (string post-processing)")
         self.db_path = db_path
@@ -55,6 +56,7 @@ class BasePipeline:
         self._encoder = encoder
         self._device = device
         self._dense_mode = dense_mode
+        self._index_build = index_build
 
     def index(self, documents: List[str], **kwargs):
         raise NotImplementedError
@@ -130,7 +132,7 @@ class BM25Pipeline(BasePipeline):
 
     def __init__(self, db_path: str = "index.duckdb", k1: float = 1.5, b: float = 0.75, **ext):
         super().__init__(db_path, **ext)
-        self.bm25 = BM25(k1=k1, b=b, device=self._device)
+        self.bm25 = BM25(k1=k1, b=b, device=self._device, index_build=self._index_build)
         self.documents: List[str] = []
 
     def index(self, documents: List[str], source_paths: List[str] = None):
@@ -162,7 +164,7 @@ class HybridBM25Pipeline(BasePipeline):
         super().__init__(db_path, **ext)
         self.semantic_weight = semantic_weight
         self.bm25_weight = bm25_weight
-        self.bm25 = BM25(device=self._device)
+        self.bm25 = BM25(device=self._device, index_build=self._index_build)
         self.documents: List[str] = []
 
     def index(self, documents: List[str], source_paths: List[str] = None, *, embeddings=None):
@@ -212,7 +214,7 @@ class MultiStagePipeline(BasePipeline):
         self.stage1_k = stage1_k
         self.stage2_k = stage2_k
         self.final_k = final_k
-        self.bm25 = BM25(device=self._device)
+        self.bm25 = BM25(device=self._device, index_build=self._index_build)
         self.documents: List[str] = []
         self._reranker = reranker
 

@@ -168,6 +168,13 @@ int hs_lexical_scores(const uint32_t* doc_chars, const int64_t* doc_off, int64_t
                       int32_t q_len, const int32_t* doc_tok, const int64_t* doc_tok_off, const int32_t* q_tok,
                       int32_t n_q_tok, int32_t q_set_size, float* out, int32_t* err_flag, void* stream);
 
+/* ---- index-time tokeniser (BM25.fit, bm25.py:58-67 / extractor.py:15-31): `text` is the lower-cased UTF-8
+ *      blob of the documents; flags[i] = 1 where a [a-z0-9_]+ token starts; hashes[t] = 63-bit hash of the
+ *      token starting at starts[t] (FNV-1a + splitmix64, host twin in index_build.py) */
+int hs_token_flags(const uint8_t* text, int64_t n_bytes, uint8_t* flags, void* stream);
+int hs_token_hashes(const uint8_t* text, int64_t n_bytes, const int64_t* starts, int64_t n_tokens, int64_t* hashes,
+                    void* stream);
+
 /* ---- synthetic corpus generators (counter-based; hybrid_search_engine_b200/synth.py is the spec) */
 int hs_synth_embeddings(float* out, int64_t row0, int64_t n, int32_t dim, int64_t ld, uint64_t seed_key,
                         void* stream);

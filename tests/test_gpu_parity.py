@@ -478,3 +478,51 @@ def test_searcher_use_faiss_semantics(hs, tmp_path):
             ids, sc = orc.search_faiss_style(ix, q, c.q_emb[qi], k)
             assert [d for _, _, d in got] == ids.tolist(), (q, k)
             assert [x for x, _, _ in got] == [float(v) for v in sc]
+
+
+NASTY_DOCS = ["", "The Quick-brown_fox's 2nd naïve café", "  a\tb\n c  ", "ÀB ſ İx KELVIN K9", "the and of",
+              "x" * 300 + " y", "tab\x00nul\x7fdel UPPER lower MiXeD 123abc _under_ __", "ümlaut-only ÿ ß",
+              "dup dup dup DUP Dup the dup", "rec\x1esep inside\x1e", "İ\x1eK"]
+
+
+@pytest.mark.parametrize("name", ["t0_sample_docs", "t1_small", "t1_mid", "nasty", "synth"])
+def test_device_index_build_equals_host_build(hs, name):
+    """index_build.py: tokeniser + hashing + CSR on the device == the host mirror of BM25.fit (bm25.py:45-81)
+    up to the renumbering of terms; the pipelines give the same bits either way."""
+    from hybrid_search_engine_b200 import synth
+    from hybrid_search_engine_b200.index import LexicalStats
+    from hybrid_search_engine_b200.index_build import DeviceLexicalStats, token_hash
+    if name == "nasty":
+        docs, queries = NASTY_DOCS, ["dup fox", "kelvin k9 x", "the", "na ve caf _under_"]
+    elif name == "synth":
+        spec = synth.SynthSpec(n_docs=3000, vocab=5000, min_len=1, max_len=60)
+        docs, queries = synth.doc_texts(spec, 0, 3000), synth.query_texts(spec, 0, 16)
+    else:
+        c = load_case(name)
+        docs, queries = c.docs, c.queries
+    for rs in (True, False):
+        h = LexicalStats(rs).fit(docs)
+        d = DeviceLexicalStats("cuda:0", rs).fit(docs, chunk_bytes=1 << 12)      # small chunks: many chunk joins
+        assert d.doc_count == h.doc_count and d.avg_doc_len == h.avg_doc_len
+        assert np.array_equal(d.doc_lengths.cpu().numpy(), h.doc_lengths)
+        assert len(d.vocab_hashes) == len(h.vocab)                                 # no hash collisions
+        assert np.all(d.vocab_hashes[1:] > d.vocab_hashes[:-1]) and (d.vocab_hashes >= 0).all()
+        ip, post = d.indptr.cpu().numpy(), d.postings.cpu().numpy()
+        for t, i in h.vocab.items():
+            hv = token_hash(t)
+            j = int(np.searchsorted(d.vocab_hashes, hv))
+            assert d.vocab_hashes[j] == hv and d.df[j] == h.df[i]
+            assert np.array_equal(post[ip[j]:ip[j + 1]].view(np.uint32), h.postings[h.indptr[i]:h.indptr[i + 1]])
+        for q in queries:
+            hq = [next(t for t, i in h.vocab.items() if i == x) for x in h.query_term_ids(q)]
+            assert [int(d.vocab_hashes[x]) for x in d.query_term_ids(q)] == [token_hash(t) for t in hq]
+    a = hs.create_pipeline("bm25")
+    b = hs.create_pipeline("bm25", index_build="device")
+    a.index(docs)
+    b.index(docs)
+    k = min(10, len(docs))
+    for ra, rb in zip(a.search_many(queries, top_k=k), b.search_many(queries, top_k=k)):
+        assert ra.results == rb.results
+    assert b.bm25.doc_lengths == a.bm25.doc_lengths
+    with pytest.raises(hs._lib.HsError):
+        b.bm25.idf
