@@ -14,6 +14,14 @@ void hs_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+__global__ void u32_max_kernel(const uint32_t* __restrict__ x, int64_t n, uint32_t* out) {
+    uint32_t m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, x[i]);
+    for (int s = 16; s >= 1; s >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, s));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
+
 extern "C" {
 
 int hs_abi_version(void) { return HS_ABI_VERSION; }
@@ -75,6 +83,23 @@ int hs_index_set_doc_stats(hs_index* idx, const uint32_t* dl, double avgdl, doub
                            const double* impact_table, uint32_t max_dl, uint32_t tf_cap) {
     HS_REQUIRE(idx != nullptr, "hs_index_set_doc_stats: idx is null");
     HS_REQUIRE(dl != nullptr || idx->n_docs == 0, "hs_index_set_doc_stats: dl is null");
+    if (impact_table != nullptr && idx->n_docs > 0) {
+        // the scoring kernels index the table by doc length without a bound check: verify the bound once here
+        // (index time, synchronous)
+        uint32_t* d_max = nullptr;
+        uint32_t h_max = 0;
+        HS_CUDA(cudaSetDevice(idx->device));
+        HS_CUDA(cudaMalloc(&d_max, sizeof(uint32_t)));
+        cudaError_t e = cudaMemset(d_max, 0, sizeof(uint32_t));
+        if (e == cudaSuccess) {
+            u32_max_kernel<<<1024, 256>>>(dl, idx->n_docs, d_max);
+            e = cudaMemcpy(&h_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        }
+        cudaFree(d_max);
+        HS_CUDA(e);
+        HS_REQUIRE(h_max <= max_dl, "hs_index_set_doc_stats: a doc length (%u) exceeds max_dl (%u)", h_max, max_dl);
+        HS_REQUIRE((uint64_t)(max_dl + 1ull) * (tf_cap + 1ull) < (1ull << 32), "hs_index_set_doc_stats: table too large");
+    }
     idx->dl = dl;
     idx->avgdl = avgdl;
     idx->k1 = k1;

@@ -22,6 +22,9 @@
 // Algorithmic bytes per query: 8 * P(q) postings + 4 * N doc lengths + 4 * N score store.
 #include "common.cuh"
 
+#include <cstdlib>
+#include <cstring>
+
 namespace {
 
 constexpr int kTileDocs = 4096;
@@ -234,6 +237,242 @@ __global__ void __launch_bounds__(kThreads, 3) bm25_tile_kernel(const Bm25Params
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Batched tile kernel (default).  One CTA owns a doc tile for up to kMaxQpc queries of the batch, one after
+// the other, which amortises the fixed costs of a tile over the queries: the slice bounds of ALL its query
+// tokens are fetched in one round trip, the doc lengths are staged once (already multiplied into impact-table
+// row offsets), and the float64 tile is re-zeroed by the epilogue that drains it.  The posting stream is
+// software-pipelined through two register buffers of kDepth postings per thread: while chunk i is gathered
+// and accumulated, the loads of chunk i+1 -- the next token's, or the next query's first token -- are in
+// flight, so DRAM latency is paid once per CTA instead of once per token.  Arithmetic, accumulation order
+// (query order per doc, one doc at most once per token) and rounding are the tile kernel's: identical bits.
+constexpr int kDepth = 8;                      // postings per thread per chunk
+constexpr int kChunkB = kThreads * kDepth;     // 2048 postings
+constexpr int kMaxQpc = 8;                     // queries per work item
+constexpr int kTokWindow = 32;                 // query tokens whose slice bounds are staged at once (one per lane)
+
+struct __align__(16) ChunkDesc {
+    int64_t off;                               // first posting of the chunk
+    int32_t len;                               // 1 .. kChunkB
+    int16_t tok, bq;                           // token (window relative) and query (CTA relative) it belongs to
+};
+
+struct BatchSmem {
+    double acc[kTileDocs];
+    uint32_t row[kTileDocs];                   // TABLE: dl * (tf_cap + 1), else dl
+    ChunkDesc chunk[2 * kTokWindow];           // a slice holds <= kTileDocs = 2 * kChunkB postings
+    double idf[kTokWindow];
+    int qoff[kMaxQpc + 1];
+    float wmax[kWarps][kMaxQpc];
+    int n_chunks;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// MODE 0: the fraction is computed per posting; 1: gathered from the impact table in global memory (L1);
+// 2: gathered from a copy of the table in shared memory.  A gather of 32 unrelated table entries costs the L1 one
+// tag lookup per cache line (32 cycles per warp instruction, which made mode 1 L1-bound at ~0.35 of the HBM
+// peak) but only ~5 bank-conflict wavefronts in shared memory -- mode 2 is the default whenever the table fits.
+// The kernel is persistent, one CTA per SM: kGroups independent 256-thread groups (named barriers), each with
+// its own tile buffers, share the one table copy and pull (tile, query group) work items round-robin.
+constexpr int kGroups = 3;
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads* kGroups, 1)
+    bm25_batch_kernel(const Bm25Params p, int B, int qpc, int n_qgroups, int table_rows) {
+    extern __shared__ __align__(16) unsigned char bm25_smem[];
+    const int grp = threadIdx.x / kThreads;
+    const int tid = threadIdx.x - grp * kThreads, lane = tid & 31, warp = tid >> 5;
+    BatchSmem& sm = reinterpret_cast<BatchSmem*>(bm25_smem)[grp];
+    double* s_table = reinterpret_cast<double*>(bm25_smem + kGroups * sizeof(BatchSmem));
+    // row stride of the shared copy: odd, so that entries of equal tf in different rows fall into different banks
+    const uint32_t width = p.tf_cap + 1;
+    const uint32_t stride = MODE == 2 ? (width | 1u) : width;
+    if (MODE == 2) {
+        for (int i = threadIdx.x; i < table_rows * (int)width; i += kThreads * kGroups) {
+            const uint32_t r = (uint32_t)i / width, c = (uint32_t)i - r * width;
+            s_table[r * stride + c] = p.impact_table[i];
+        }
+    }
+    for (int j = tid; j < kTileDocs; j += kThreads) sm.acc[j] = 0.0;
+    __syncthreads();
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kThreads) : "memory"); };
+    const uint32_t tbl_s = (uint32_t)__cvta_generic_to_shared(s_table);
+    const int64_t n_items = (int64_t)p.n_tiles * n_qgroups;
+
+    for (int64_t item = (int64_t)blockIdx.x * kGroups + grp; item < n_items; item += (int64_t)gridDim.x * kGroups) {
+        const int tile = (int)(item / n_qgroups);
+        const int b0 = (int)(item - (int64_t)tile * n_qgroups) * qpc;
+        const int nb = (B - b0 < qpc) ? (B - b0) : qpc;
+        const int64_t d_lo = (int64_t)tile * kTileDocs;
+        const int ndoc = (int)((d_lo + kTileDocs < p.n_docs ? d_lo + kTileDocs : p.n_docs) - d_lo);
+        // shared-memory addresses pre-biased by the tile's first doc id: slot of doc x = base + x * size (mod 2^32)
+        const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(sm.acc) - (uint32_t)d_lo * 8u;
+        const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(sm.row) - (uint32_t)d_lo * 4u;
+
+        for (int j = tid; j < ndoc; j += kThreads) {
+            const uint32_t dl = p.dl[d_lo + j];
+            sm.row[j] = MODE != 0 ? dl * stride : dl;
+        }
+        if (tid <= nb) sm.qoff[tid] = p.q_off[b0 + tid];
+        if (tid < kMaxQpc)
+            for (int w = 0; w < kWarps; ++w) sm.wmax[w][tid] = 0.0f;
+        gsync();
+        const int T0 = sm.qoff[0], T1 = sm.qoff[nb];
+
+        int bq = 0;                                // query (relative to b0) whose partial scores are in the tile
+        // drains the tile into the score row of query bq: float64 -> float32 once, coalesced store, re-zero, max
+        auto epilogue = [&]() {
+            float mx = 0.0f;
+            float* o = p.scores + (int64_t)(b0 + bq) * p.n_docs + d_lo;
+            if (ndoc == kTileDocs && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {     // group-uniform: full tile
+                double2* a2 = reinterpret_cast<double2*>(sm.acc) + tid;
+                float2* o2 = reinterpret_cast<float2*>(o) + tid;
+#pragma unroll
+                for (int r = 0; r < kTileDocs / (2 * kThreads); ++r) {
+                    const double2 a = a2[r * kThreads];
+                    a2[r * kThreads] = make_double2(0.0, 0.0);
+                    const float s0 = __double2float_rn(a.x), s1 = __double2float_rn(a.y);
+                    o2[r * kThreads] = make_float2(s0, s1);
+                    mx = fmaxf(mx, fmaxf(s0, s1));
+                }
+            } else {
+                for (int j = tid; j < ndoc; j += kThreads) {
+                    const float sc = __double2float_rn(sm.acc[j]);
+                    sm.acc[j] = 0.0;
+                    o[j] = sc;
+                    mx = fmaxf(mx, sc);
+                }
+            }
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+            if (lane == 0) sm.wmax[warp][bq] = mx;
+            gsync();
+        };
+        // A chunk is loaded and consumed by one of three group-uniform code paths: full (kChunkB postings, no
+        // predicates at all), short (<= kThreads postings: one predicated slot) or general.
+        auto load_chunk = [&](int64_t off, int len, uint2 (&buf)[kDepth]) {
+            const uint2* pp = p.postings + off + tid;
+            if (len == kChunkB) {
+#pragma unroll
+                for (int u = 0; u < kDepth; ++u) buf[u] = __ldg(pp + u * kThreads);
+            } else if (len <= kThreads) {
+                if (tid < len) buf[0] = __ldg(pp);
+            } else {
+#pragma unroll
+                for (int u = 0; u < kDepth; ++u)
+                    if (tid + u * kThreads < len) buf[u] = __ldg(pp + u * kThreads);
+            }
+        };
+        auto frac_of = [&](uint32_t r, uint32_t tf) -> double {
+            if (MODE == 2 && tf <= p.tf_cap) return lds_f64(tbl_s + (r + tf) * 8u);
+            if (MODE == 1 && tf <= p.tf_cap) return __ldg(p.impact_table + (r + tf));
+            return bm25_frac_compute(p.k1, p.one_minus_b, p.b, p.avgdl, p.k1p1, tf, MODE != 0 ? r / stride : r);
+        };
+        auto consume = [&](int ci, const uint2 (&buf)[kDepth]) {
+            const ChunkDesc d = sm.chunk[ci];
+            while (bq < d.bq) {                                                  // earlier queries are complete
+                epilogue();
+                ++bq;
+            }
+            const double idf = sm.idf[d.tok];
+            if (d.len == kChunkB) {
+#pragma unroll
+                for (int h = 0; h < kDepth; h += 4) {
+                    double fr[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) fr[u] = frac_of(lds_u32(row_s + buf[h + u].x * 4u), buf[h + u].y);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint32_t a = acc_s + buf[h + u].x * 8u;
+                        sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, fr[u])));
+                    }
+                }
+            } else if (d.len <= kThreads) {
+                if (tid < d.len) {
+                    const double f = frac_of(lds_u32(row_s + buf[0].x * 4u), buf[0].y);
+                    const uint32_t a = acc_s + buf[0].x * 8u;
+                    sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < kDepth; ++u) {
+                    if (tid + u * kThreads < d.len) {
+                        const double f = frac_of(lds_u32(row_s + buf[u].x * 4u), buf[u].y);
+                        const uint32_t a = acc_s + buf[u].x * 8u;
+                        sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
+                    }
+                }
+            }
+            gsync();                                         // token order: these updates land before the next token's
+        };
+
+        for (int w0 = T0; w0 < T1; w0 += kTokWindow) {
+            // ---- warp 0 turns the next <= 32 query tokens into a list of posting chunks for this doc tile
+            if (warp == 0) {
+                const int t = w0 + lane;
+                int64_t lo = 0, hi = 0;
+                if (t < T1) {
+                    const int64_t* r = p.ranges + (int64_t)t * (p.n_tiles + 1) + tile;
+                    lo = r[0];
+                    hi = r[1];
+                    sm.idf[lane] = p.q_idf[t];
+                }
+                const int len = (int)(hi - lo);                  // <= kTileDocs: a doc occurs once per posting list
+                const int n = (len + kChunkB - 1) / kChunkB;
+                int incl = n;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, dlt);
+                    if (lane >= dlt) incl += v;
+                }
+                int q = 0;
+                for (int i = 1; i < nb; ++i) q += (t >= sm.qoff[i]);
+                for (int c = 0; c < n; ++c) {
+                    ChunkDesc d;
+                    d.off = lo + (int64_t)c * kChunkB;
+                    d.len = len - c * kChunkB < kChunkB ? len - c * kChunkB : kChunkB;
+                    d.tok = (int16_t)lane;
+                    d.bq = (int16_t)q;
+                    sm.chunk[incl - n + c] = d;
+                }
+                if (lane == 31) sm.n_chunks = incl;
+            }
+            gsync();
+            const int nC = sm.n_chunks;
+            uint2 A[kDepth], Bf[kDepth];
+            if (nC > 0) load_chunk(sm.chunk[0].off, sm.chunk[0].len, A);
+            for (int i = 0; i < nC; i += 2) {
+                if (i + 1 < nC) load_chunk(sm.chunk[i + 1].off, sm.chunk[i + 1].len, Bf);
+                consume(i, A);
+                if (i + 1 >= nC) break;
+                if (i + 2 < nC) load_chunk(sm.chunk[i + 2].off, sm.chunk[i + 2].len, A);
+                consume(i + 1, Bf);
+            }
+            gsync();     // the window's chunk list and idf values may be overwritten
+        }
+        for (; bq < nb; ++bq) epilogue();                    // the last query, and queries without known tokens
+        if (p.stats != nullptr && tid < nb) {
+            float v = sm.wmax[0][tid];
+            for (int w = 1; w < kWarps; ++w) v = fmaxf(v, sm.wmax[w][tid]);
+            atomicMax(&p.stats[(b0 + tid) * 4 + HS_STAT_MAX_B], hs_enc_f32(v));
+        }
+        gsync();         // wmax / qoff / row are rewritten by the next item
+    }
+}
+
 // BM25Plus (bm25.py:150-179): every doc receives idf * (num / den + delta) for every known query token,
 // tf = 0 included (num / den = 0 there), so the variant is dense.  Same tiling; per token the posting slice
 // is first scattered into a second float64 tile (sentinel -1 = no posting), then ALL docs of the tile are
@@ -384,6 +623,25 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     return HS_OK;
 }
 
+// HS_BM25_IMPL=tile selects the one-query-per-CTA tile kernel (A/B measurements); both give the same bits.
+// 0 compute, 1 table in global memory, 2 table in shared memory (HS_BM25_TABLE=global forces 1 for A/B runs)
+int bm25_table_mode(bool have_table, size_t smem_with_table) {
+    static const bool force_global = [] {
+        const char* e = getenv("HS_BM25_TABLE");
+        return e != nullptr && strcmp(e, "global") == 0;
+    }();
+    if (!have_table) return 0;
+    return (!force_global && smem_with_table <= 227 * 1024) ? 2 : 1;
+}
+
+bool bm25_use_batch() {
+    static const bool tile = [] {
+        const char* e = getenv("HS_BM25_IMPL");
+        return e != nullptr && strcmp(e, "tile") == 0;
+    }();
+    return !tile;
+}
+
 }  // namespace
 
 extern "C" {
@@ -432,6 +690,26 @@ static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const do
         const size_t smem = (size_t)kTileDocs * (2 * sizeof(double) + sizeof(uint32_t));
         HS_CUDA(cudaFuncSetAttribute(bm25plus_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         bm25plus_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+    } else if (bm25_use_batch()) {
+        // queries per work item: as many as possible (<= kMaxQpc) while there are a few items per group
+        const int sms = hs_num_sms(idx->device);
+        int qpc = B < kMaxQpc ? B : kMaxQpc;
+        while (qpc > 1 && (int64_t)p.n_tiles * ((B + qpc - 1) / qpc) < (int64_t)8 * kGroups * sms) qpc = (qpc + 1) / 2;
+        const int nqg = (B + qpc - 1) / qpc;
+        const int64_t n_items = (int64_t)p.n_tiles * nqg;
+        const int64_t rows = p.impact_table != nullptr ? (int64_t)p.max_dl + 1 : 0;
+        const size_t tbl_bytes = (size_t)rows * ((p.tf_cap + 1) | 1u) * sizeof(double);
+        const size_t base = kGroups * sizeof(BatchSmem);
+        const int mode = bm25_table_mode(p.impact_table != nullptr, base + tbl_bytes);
+        const size_t smem = base + (mode == 2 ? tbl_bytes : 0);
+        const unsigned grid = (unsigned)((n_items + kGroups - 1) / kGroups < sms ? (n_items + kGroups - 1) / kGroups : sms);
+        auto launch = [&](auto kern) -> int {
+            HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, kThreads * kGroups, smem, (cudaStream_t)stream>>>(p, B, qpc, nqg, (int)rows);
+            return HS_OK;
+        };
+        rc = mode == 2 ? launch(bm25_batch_kernel<2>) : (mode == 1 ? launch(bm25_batch_kernel<1>) : launch(bm25_batch_kernel<0>));
+        if (rc != HS_OK) return rc;
     } else {
         const size_t smem = (size_t)kTileDocs * (sizeof(double) + sizeof(uint32_t));
         HS_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
