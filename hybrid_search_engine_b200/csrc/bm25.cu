@@ -246,8 +246,10 @@ __global__ void __launch_bounds__(kThreads, 3) bm25_tile_kernel(const Bm25Params
 // and accumulated, the loads of chunk i+1 -- the next token's, or the next query's first token -- are in
 // flight, so DRAM latency is paid once per CTA instead of once per token.  Arithmetic, accumulation order
 // (query order per doc, one doc at most once per token) and rounding are the tile kernel's: identical bits.
+constexpr int kBThreads = 256;                 // threads per group of the batched kernel
+constexpr int kBWarps = kBThreads / 32;
 constexpr int kDepth = 8;                      // postings per thread per chunk
-constexpr int kChunkB = kThreads * kDepth;     // 2048 postings
+constexpr int kChunkB = kBThreads * kDepth;     // 2048 postings
 constexpr int kMaxQpc = 8;                     // queries per work item
 constexpr int kTokWindow = 32;                 // query tokens whose slice bounds are staged at once (one per lane)
 
@@ -263,7 +265,7 @@ struct BatchSmem {
     ChunkDesc chunk[2 * kTokWindow];           // a slice holds <= kTileDocs = 2 * kChunkB postings
     double idf[kTokWindow];
     int qoff[kMaxQpc + 1];
-    float wmax[kWarps][kMaxQpc];
+    float wmax[kBWarps][kMaxQpc];
     int n_chunks;
 };
 
@@ -290,29 +292,34 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
 constexpr int kGroups = 3;
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads* kGroups, 1)
+__global__ void __launch_bounds__(kBThreads* kGroups, 1)
     bm25_batch_kernel(const Bm25Params p, int B, int qpc, int n_qgroups, int table_rows) {
     extern __shared__ __align__(16) unsigned char bm25_smem[];
-    const int grp = threadIdx.x / kThreads;
-    const int tid = threadIdx.x - grp * kThreads, lane = tid & 31, warp = tid >> 5;
+    const int grp = threadIdx.x / kBThreads;
+    const int tid = threadIdx.x - grp * kBThreads, lane = tid & 31, warp = tid >> 5;
     BatchSmem& sm = reinterpret_cast<BatchSmem*>(bm25_smem)[grp];
     double* s_table = reinterpret_cast<double*>(bm25_smem + kGroups * sizeof(BatchSmem));
     // row stride of the shared copy: odd, so that entries of equal tf in different rows fall into different banks
     const uint32_t width = p.tf_cap + 1;
     const uint32_t stride = MODE == 2 ? (width | 1u) : width;
     if (MODE == 2) {
-        for (int i = threadIdx.x; i < table_rows * (int)width; i += kThreads * kGroups) {
+        for (int i = threadIdx.x; i < table_rows * (int)width; i += kBThreads * kGroups) {
             const uint32_t r = (uint32_t)i / width, c = (uint32_t)i - r * width;
             s_table[r * stride + c] = p.impact_table[i];
         }
     }
-    for (int j = tid; j < kTileDocs; j += kThreads) sm.acc[j] = 0.0;
+    for (int j = tid; j < kTileDocs; j += kBThreads) sm.acc[j] = 0.0;
     __syncthreads();
-    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kThreads) : "memory"); };
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kBThreads) : "memory"); };
     const uint32_t tbl_s = (uint32_t)__cvta_generic_to_shared(s_table);
     const int64_t n_items = (int64_t)p.n_tiles * n_qgroups;
 
-    for (int64_t item = (int64_t)blockIdx.x * kGroups + grp; item < n_items; item += (int64_t)gridDim.x * kGroups) {
+    // every group takes a contiguous run of items (tile-major): consecutive items mostly share the doc tile, so
+    // its doc lengths are staged once per tile, and the runs differ by at most one item
+    const int64_t n_workers = (int64_t)gridDim.x * kGroups, me = (int64_t)blockIdx.x * kGroups + grp;
+    const int64_t item_lo = n_items * me / n_workers, item_hi = n_items * (me + 1) / n_workers;
+    int staged_tile = -1;
+    for (int64_t item = item_lo; item < item_hi; ++item) {
         const int tile = (int)(item / n_qgroups);
         const int b0 = (int)(item - (int64_t)tile * n_qgroups) * qpc;
         const int nb = (B - b0 < qpc) ? (B - b0) : qpc;
@@ -322,13 +329,16 @@ __global__ void __launch_bounds__(kThreads* kGroups, 1)
         const uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(sm.acc) - (uint32_t)d_lo * 8u;
         const uint32_t row_s = (uint32_t)__cvta_generic_to_shared(sm.row) - (uint32_t)d_lo * 4u;
 
-        for (int j = tid; j < ndoc; j += kThreads) {
-            const uint32_t dl = p.dl[d_lo + j];
-            sm.row[j] = MODE != 0 ? dl * stride : dl;
+        if (tile != staged_tile) {
+            for (int j = tid; j < ndoc; j += kBThreads) {
+                const uint32_t dl = p.dl[d_lo + j];
+                sm.row[j] = MODE != 0 ? dl * stride : dl;
+            }
+            staged_tile = tile;
         }
         if (tid <= nb) sm.qoff[tid] = p.q_off[b0 + tid];
         if (tid < kMaxQpc)
-            for (int w = 0; w < kWarps; ++w) sm.wmax[w][tid] = 0.0f;
+            for (int w = 0; w < kBWarps; ++w) sm.wmax[w][tid] = 0.0f;
         gsync();
         const int T0 = sm.qoff[0], T1 = sm.qoff[nb];
 
@@ -341,15 +351,15 @@ __global__ void __launch_bounds__(kThreads* kGroups, 1)
                 double2* a2 = reinterpret_cast<double2*>(sm.acc) + tid;
                 float2* o2 = reinterpret_cast<float2*>(o) + tid;
 #pragma unroll
-                for (int r = 0; r < kTileDocs / (2 * kThreads); ++r) {
-                    const double2 a = a2[r * kThreads];
-                    a2[r * kThreads] = make_double2(0.0, 0.0);
+                for (int r = 0; r < kTileDocs / (2 * kBThreads); ++r) {
+                    const double2 a = a2[r * kBThreads];
+                    a2[r * kBThreads] = make_double2(0.0, 0.0);
                     const float s0 = __double2float_rn(a.x), s1 = __double2float_rn(a.y);
-                    o2[r * kThreads] = make_float2(s0, s1);
+                    o2[r * kBThreads] = make_float2(s0, s1);
                     mx = fmaxf(mx, fmaxf(s0, s1));
                 }
             } else {
-                for (int j = tid; j < ndoc; j += kThreads) {
+                for (int j = tid; j < ndoc; j += kBThreads) {
                     const float sc = __double2float_rn(sm.acc[j]);
                     sm.acc[j] = 0.0;
                     o[j] = sc;
@@ -362,18 +372,18 @@ __global__ void __launch_bounds__(kThreads* kGroups, 1)
             gsync();
         };
         // A chunk is loaded and consumed by one of three group-uniform code paths: full (kChunkB postings, no
-        // predicates at all), short (<= kThreads postings: one predicated slot) or general.
+        // predicates at all), short (<= kBThreads postings: one predicated slot) or general.
         auto load_chunk = [&](int64_t off, int len, uint2 (&buf)[kDepth]) {
             const uint2* pp = p.postings + off + tid;
             if (len == kChunkB) {
 #pragma unroll
-                for (int u = 0; u < kDepth; ++u) buf[u] = __ldg(pp + u * kThreads);
-            } else if (len <= kThreads) {
+                for (int u = 0; u < kDepth; ++u) buf[u] = __ldg(pp + u * kBThreads);
+            } else if (len <= kBThreads) {
                 if (tid < len) buf[0] = __ldg(pp);
             } else {
 #pragma unroll
                 for (int u = 0; u < kDepth; ++u)
-                    if (tid + u * kThreads < len) buf[u] = __ldg(pp + u * kThreads);
+                    if (tid + u * kBThreads < len) buf[u] = __ldg(pp + u * kBThreads);
             }
         };
         auto frac_of = [&](uint32_t r, uint32_t tf) -> double {
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(kThreads* kGroups, 1)
                         sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, fr[u])));
                     }
                 }
-            } else if (d.len <= kThreads) {
+            } else if (d.len <= kBThreads) {
                 if (tid < d.len) {
                     const double f = frac_of(lds_u32(row_s + buf[0].x * 4u), buf[0].y);
                     const uint32_t a = acc_s + buf[0].x * 8u;
@@ -409,7 +419,7 @@ __global__ void __launch_bounds__(kThreads* kGroups, 1)
             } else {
 #pragma unroll
                 for (int u = 0; u < kDepth; ++u) {
-                    if (tid + u * kThreads < d.len) {
+                    if (tid + u * kBThreads < d.len) {
                         const double f = frac_of(lds_u32(row_s + buf[u].x * 4u), buf[u].y);
                         const uint32_t a = acc_s + buf[u].x * 8u;
                         sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
@@ -466,7 +476,7 @@ __global__ void __launch_bounds__(kThreads* kGroups, 1)
         for (; bq < nb; ++bq) epilogue();                    // the last query, and queries without known tokens
         if (p.stats != nullptr && tid < nb) {
             float v = sm.wmax[0][tid];
-            for (int w = 1; w < kWarps; ++w) v = fmaxf(v, sm.wmax[w][tid]);
+            for (int w = 1; w < kBWarps; ++w) v = fmaxf(v, sm.wmax[w][tid]);
             atomicMax(&p.stats[(b0 + tid) * 4 + HS_STAT_MAX_B], hs_enc_f32(v));
         }
         gsync();         // wmax / qoff / row are rewritten by the next item
@@ -705,7 +715,7 @@ static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const do
         const unsigned grid = (unsigned)((n_items + kGroups - 1) / kGroups < sms ? (n_items + kGroups - 1) / kGroups : sms);
         auto launch = [&](auto kern) -> int {
             HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kThreads * kGroups, smem, (cudaStream_t)stream>>>(p, B, qpc, nqg, (int)rows);
+            kern<<<grid, kBThreads * kGroups, smem, (cudaStream_t)stream>>>(p, B, qpc, nqg, (int)rows);
             return HS_OK;
         };
         rc = mode == 2 ? launch(bm25_batch_kernel<2>) : (mode == 1 ? launch(bm25_batch_kernel<1>) : launch(bm25_batch_kernel<0>));
