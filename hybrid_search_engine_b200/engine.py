@@ -53,6 +53,7 @@ class SearchEngine:
         self.max_batch = int(max_batch)
         self.dense_mode = dense_mode
         self._bufs = {}
+        self._pin_slot = 0         # which set of pinned staging buffers the uploads use (search_*_stream)
         self.launches = 0          # kernels launched by this engine (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------ buffers (never on the hot path twice)
@@ -66,7 +67,7 @@ class SearchEngine:
 
     def _pinned(self, name: str, shape, dtype) -> torch.Tensor:
         need = int(np.prod(shape)) if len(shape) else 1
-        key = "pin_" + name
+        key = f"pin{self._pin_slot}_{name}"
         t = self._bufs.get(key)
         if t is None or t.numel() < need or t.dtype != dtype:
             t = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
@@ -244,6 +245,40 @@ class SearchEngine:
     def search_hybrid_bm25(self, qb: QueryBatch, k: int, ws: float, wl: float, dense_mode: Optional[str] = None):
         """HybridBM25Pipeline.search (pipelines.py:315-357) for a batch.  -> (scores [B,k], ids [B,k])."""
         return self._run(qb, k, HS_FUSE_HYBRID_BM25, ws, wl, True, True, dense_mode)
+
+    def search_hybrid_bm25_stream(self, batches, k: int, ws: float, wl: float, dense_mode: Optional[str] = None,
+                                  depth: int = 2):
+        """Serving loop over an iterable of QueryBatch: yields (scores, ids) as numpy arrays, in order.
+
+        Nothing here waits for the GPU except the hand-over of a finished result: while batch i runs, the host
+        flattens and uploads batch i+1 from a second set of pinned staging buffers, and batch i's top-k is
+        copied back asynchronously into pinned memory.  Same kernels and bits as ``search_hybrid_bm25``."""
+        from collections import deque
+        pending = deque()
+
+        def collect(item):
+            ev, hs, hi = item
+            ev.synchronize()
+            return hs.numpy().copy(), hi.numpy().copy()
+
+        try:
+            for n, qb in enumerate(batches):
+                if len(pending) == depth:          # the slot reused below must have been drained
+                    yield collect(pending.popleft())
+                self._pin_slot = n % depth
+                sc, ids = self.search_hybrid_bm25(qb, k, ws, wl, dense_mode)
+                with torch.cuda.device(self.device):
+                    hs = self._pinned("out_s", tuple(sc.shape), sc.dtype)
+                    hi = self._pinned("out_i", tuple(ids.shape), ids.dtype)
+                    hs.copy_(sc, non_blocking=True)
+                    hi.copy_(ids, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                pending.append((ev, hs, hi))
+            while pending:
+                yield collect(pending.popleft())
+        finally:
+            self._pin_slot = 0
 
     def search_semantic(self, qb: QueryBatch, k: int, sw: float = 1.0, dense_mode: Optional[str] = None):
         """Searcher.search with lexical weight 0 (pipelines.py:317-324,474-481): min-max cosine * sw."""

@@ -526,3 +526,27 @@ def test_device_index_build_equals_host_build(hs, name):
     assert b.bm25.doc_lengths == a.bm25.doc_lengths
     with pytest.raises(hs._lib.HsError):
         b.bm25.idf
+
+
+def test_serving_loop_equals_single_batches(hs):
+    """search_hybrid_bm25_stream (pipelined uploads / async result copies) returns, batch for batch, the bits of
+    search_hybrid_bm25."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=50_000, vocab=20_000, dim=64)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, "cuda:0")
+    eng = SearchEngine(shard, max_batch=8)
+    th = synth.zipf_thresholds(spec.vocab)
+    batches = []
+    for i, B in enumerate([8, 3, 8, 1, 5, 8, 8]):
+        batches.append(QueryBatch(vectors=synth.query_embeddings(spec, 10 * i, 10 * i + B),
+                                  term_ids=synth.query_terms(spec, 10 * i, 10 * i + B, th).tolist()))
+    want = []
+    for qb in batches:
+        sc, ids = eng.search_hybrid_bm25(qb, 50, 0.6, 0.4)
+        want.append((sc.cpu().numpy().copy(), ids.cpu().numpy().copy()))
+    got = list(eng.search_hybrid_bm25_stream(batches, 50, 0.6, 0.4))
+    assert len(got) == len(want)
+    for (gs, gi), (ws, wi) in zip(got, want):
+        assert np.array_equal(gi, wi) and np.array_equal(gs, ws)
+    assert list(eng.search_hybrid_bm25_stream([], 50, 0.6, 0.4)) == []
