@@ -8,7 +8,7 @@ ap.add_argument("--n-docs", type=int, default=4_000_000)
 ap.add_argument("--child", default="")
 a = ap.parse_args()
 if not a.child:
-    for impl in ("tile", "stream"):
+    for impl in ("tile", "batch"):
         env = dict(os.environ, HS_BM25_IMPL=impl)
         subprocess.run([sys.executable, __file__, "--n-docs", str(a.n_docs), "--child", impl], env=env, check=True)
     sys.exit(0)
