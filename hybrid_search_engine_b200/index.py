@@ -125,8 +125,13 @@ class DeviceIndex:
             st = stream_ptr(self.device)
             self.impact_table, self.tf_cap = None, 0
             if avgdl > 0 and self.max_dl < (1 << 20):
-                # table of <= 8 MB: 31 tf columns for ordinary doc lengths, fewer for very long docs
+                # widest table whose shared-memory copy (odd row stride, ~10 000 doubles next to the three tile
+                # buffers of bm25_batch_kernel) still fits; else a table of <= 8 MB gathered through L1
                 self.tf_cap = 31 if self.max_dl < (1 << 15) else (7 if self.max_dl < (1 << 17) else 0)
+                for cap in (31, 15, 7, 3):
+                    if (self.max_dl + 1) * ((cap + 1) | 1) <= 10_000:
+                        self.tf_cap = cap
+                        break
                 self.impact_table = torch.empty((self.max_dl + 1) * (self.tf_cap + 1), dtype=torch.float64,
                                                 device=self.device)
                 check(self.lib.hs_bm25_impact_table(float(avgdl), self.k1, self.b, self.max_dl, self.tf_cap,

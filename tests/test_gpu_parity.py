@@ -550,3 +550,61 @@ def test_serving_loop_equals_single_batches(hs):
     for (gs, gi), (ws, wi) in zip(got, want):
         assert np.array_equal(gi, wi) and np.array_equal(gs, ws)
     assert list(eng.search_hybrid_bm25_stream([], 50, 0.6, 0.4)) == []
+
+
+@pytest.mark.parametrize("max_len,tf_hi", [(60, 4), (900, 100)])
+def test_bm25_batched_kernel_shapes(hs, max_len, tf_hi):
+    """The batched BM25 kernel against a float64 restatement of bm25.py:99-110 (same operation order) on a
+    CSR built directly: ragged last tile, odd doc count (unaligned score rows), 19 queries (several work items per
+    tile), a 70-token query (three token windows), empty / unknown-only queries in the middle of the batch,
+    duplicates, an odd total posting count, tf beyond the table's columns, and -- second case -- doc lengths too
+    long for the shared-memory copy of the impact table (table gathered from global memory)."""
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    from hybrid_search_engine_b200.index import DeviceIndex, idf_from_df
+    rng = np.random.default_rng(7 + max_len)
+    n, V = 2 * 4096 + 905, 40
+    dens = np.concatenate([[1.0, 0.97, 0.6, 0.3], rng.uniform(0.0005, 0.05, V - 4)])
+    indptr, pd, ptf = [0], [], []
+    for t in range(V):
+        docs = np.flatnonzero(rng.random(n) < dens[t])
+        if t == 5:
+            docs = np.array([4095, 4096, n - 1])
+        pd.append(docs)
+        ptf.append(rng.integers(1, tf_hi + 1, len(docs)))
+        indptr.append(indptr[-1] + len(docs))
+    if indptr[-1] % 2 == 0:                                   # make the posting count odd
+        pd[-1] = pd[-1][:-1]; ptf[-1] = ptf[-1][:-1]; indptr[-1] -= 1
+    pd, ptf = np.concatenate(pd), np.concatenate(ptf)
+    dl = rng.integers(0, max_len + 1, n)
+    avgdl = float(dl.sum()) / n
+    df = np.diff(indptr)
+    k1, b = 1.5, 0.75
+    shard = DeviceIndex("cuda:0", n)
+    shard.set_bm25(torch.from_numpy(np.asarray(indptr, np.int64)),
+                   torch.from_numpy(np.stack([pd, ptf], 1).astype(np.uint32).view(np.int32)),
+                   torch.from_numpy(dl.astype(np.int32)), avgdl, df, n, k1, b)
+    eng = SearchEngine(shard, max_batch=32)
+    queries = [list(rng.integers(0, V, rng.integers(1, 7))) for _ in range(19)]
+    queries[3] = []
+    queries[4] = [V + 5, -1]                                   # unknown terms only
+    queries[7] = list(rng.integers(0, V, 70))
+    queries[8] = [0, 0, 1, 0]
+    queries[18] = [5]
+    idf = idf_from_df(n, df)
+    want = np.zeros((len(queries), n), np.float64)
+    kd = k1 * ((1 - b) + b * (dl.astype(np.float64) / avgdl))
+    for qi, q in enumerate(queries):
+        for t in q:
+            if not (0 <= t < V) or df[t] == 0:
+                continue
+            d, tf = pd[indptr[t]:indptr[t + 1]], ptf[indptr[t]:indptr[t + 1]].astype(np.float64)
+            den = tf + kd[d]
+            want[qi, d] += idf[t] * np.where(den > 0, (tf * (k1 + 1)) / np.where(den > 0, den, 1.0), 0.0)
+    qt, qi_, qo = eng.upload_terms(queries)
+    stats = eng._stats(len(queries))
+    got = eng.bm25_score(qt, qi_, qo, len(queries), stats).cpu().numpy()
+    assert np.array_equal(got, want.astype(np.float32))
+    from hybrid_search_engine_b200._lib import check, load, ptr, stream_ptr
+    f = torch.empty((len(queries), 4), dtype=torch.float32, device="cuda:0")
+    check(load().hs_stats_decode(ptr(stats), ptr(f), len(queries), stream_ptr(f.device)))
+    assert np.array_equal(f.cpu().numpy()[:, 2], want.astype(np.float32).max(axis=1))      # HS_STAT_MAX_B
