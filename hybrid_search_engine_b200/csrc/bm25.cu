@@ -319,10 +319,15 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
     const int64_t n_workers = (int64_t)gridDim.x * kGroups, me = (int64_t)blockIdx.x * kGroups + grp;
     const int64_t item_lo = n_items * me / n_workers, item_hi = n_items * (me + 1) / n_workers;
     int staged_tile = -1;
-    for (int64_t item = item_lo; item < item_hi; ++item) {
+    for (int64_t item = item_lo; item < item_hi;) {
+        // merge the run's consecutive items of one tile into a single pass over up to kMaxQpc queries
         const int tile = (int)(item / n_qgroups);
-        const int b0 = (int)(item - (int64_t)tile * n_qgroups) * qpc;
-        const int nb = (B - b0 < qpc) ? (B - b0) : qpc;
+        const int qg = (int)(item - (int64_t)tile * n_qgroups);
+        int qg_end = (item_hi - item < (int64_t)(n_qgroups - qg)) ? qg + (int)(item_hi - item) : n_qgroups;
+        if ((qg_end - qg) * qpc > kMaxQpc) qg_end = qg + kMaxQpc / qpc;
+        const int b0 = qg * qpc;
+        const int nb = (B < qg_end * qpc ? B : qg_end * qpc) - b0;
+        item += qg_end - qg;
         const int64_t d_lo = (int64_t)tile * kTileDocs;
         const int ndoc = (int)((d_lo + kTileDocs < p.n_docs ? d_lo + kTileDocs : p.n_docs) - d_lo);
         // shared-memory addresses pre-biased by the tile's first doc id: slot of doc x = base + x * size (mod 2^32)
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
         if (tile != staged_tile) {
             for (int j = tid; j < ndoc; j += kBThreads) {
                 const uint32_t dl = p.dl[d_lo + j];
-                sm.row[j] = MODE != 0 ? dl * stride : dl;
+                sm.row[j] = MODE == 2 ? tbl_s + dl * stride * 8u : (MODE == 1 ? dl * stride : dl);
             }
             staged_tile = tile;
         }
@@ -386,10 +391,27 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
                     if (tid + u * kBThreads < len) buf[u] = __ldg(pp + u * kBThreads);
             }
         };
-        auto frac_of = [&](uint32_t r, uint32_t tf) -> double {
-            if (MODE == 2 && tf <= p.tf_cap) return lds_f64(tbl_s + (r + tf) * 8u);
-            if (MODE == 1 && tf <= p.tf_cap) return __ldg(p.impact_table + (r + tf));
-            return bm25_frac_compute(p.k1, p.one_minus_b, p.b, p.avgdl, p.k1p1, tf, MODE != 0 ? r / stride : r);
+        // r: what sm.row holds for the doc (MODE 2: shared-memory address of its table row, MODE 1: row index
+        // times the row stride, MODE 0: the doc length)
+        // one thread asks the L2 for the chunk after next (16-byte aligned range inside the slice), so that the
+        // register loads issued one chunk ahead find their lines on chip
+        auto prefetch_chunk = [&](int ci) {
+            if (tid == 0) {
+                const ChunkDesc d = sm.chunk[ci];
+                const int64_t lo = (d.off + 1) & ~(int64_t)1, hi = (d.off + d.len) & ~(int64_t)1;
+                if (hi > lo)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.postings + lo),
+                                 "r"((uint32_t)(hi - lo) * 8u)
+                                 : "memory");
+            }
+        };
+        auto frac_fast = [&](uint32_t r, uint32_t tf) -> double {                 // requires tf <= tf_cap
+            return MODE == 2 ? lds_f64(r + tf * 8u) : __ldg(p.impact_table + (r + tf));
+        };
+        auto frac_any = [&](uint32_t r, uint32_t tf) -> double {
+            if (MODE != 0 && tf <= p.tf_cap) return frac_fast(r, tf);
+            const uint32_t dl = MODE == 2 ? (r - tbl_s) / (stride * 8u) : (MODE == 1 ? r / stride : r);
+            return bm25_frac_compute(p.k1, p.one_minus_b, p.b, p.avgdl, p.k1p1, tf, dl);
         };
         auto consume = [&](int ci, const uint2 (&buf)[kDepth]) {
             const ChunkDesc d = sm.chunk[ci];
@@ -399,20 +421,33 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
             }
             const double idf = sm.idf[d.tok];
             if (d.len == kChunkB) {
+                // one test per thread instead of one per posting: the OR of the tfs bounds their maximum
+                uint32_t tf_or = 0;
+#pragma unroll
+                for (int u = 0; u < kDepth; ++u) tf_or |= buf[u].y;
+                const bool fast = MODE != 0 && tf_or <= p.tf_cap;
 #pragma unroll
                 for (int h = 0; h < kDepth; h += 4) {
-                    double fr[4];
+                    double fr[4], cur[4];
+                    uint32_t r[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) fr[u] = frac_of(lds_u32(row_s + buf[h + u].x * 4u), buf[h + u].y);
+                    for (int u = 0; u < 4; ++u) r[u] = lds_u32(row_s + buf[h + u].x * 4u);
+                    if (fast) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint32_t a = acc_s + buf[h + u].x * 8u;
-                        sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, fr[u])));
+                        for (int u = 0; u < 4; ++u) fr[u] = frac_fast(r[u], buf[h + u].y);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) fr[u] = frac_any(r[u], buf[h + u].y);
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) cur[u] = lds_f64(acc_s + buf[h + u].x * 8u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        sts_f64(acc_s + buf[h + u].x * 8u, __dadd_rn(cur[u], __dmul_rn(idf, fr[u])));
                 }
             } else if (d.len <= kBThreads) {
                 if (tid < d.len) {
-                    const double f = frac_of(lds_u32(row_s + buf[0].x * 4u), buf[0].y);
+                    const double f = frac_any(lds_u32(row_s + buf[0].x * 4u), buf[0].y);
                     const uint32_t a = acc_s + buf[0].x * 8u;
                     sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
                 }
@@ -420,7 +455,7 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
 #pragma unroll
                 for (int u = 0; u < kDepth; ++u) {
                     if (tid + u * kBThreads < d.len) {
-                        const double f = frac_of(lds_u32(row_s + buf[u].x * 4u), buf[u].y);
+                        const double f = frac_any(lds_u32(row_s + buf[u].x * 4u), buf[u].y);
                         const uint32_t a = acc_s + buf[u].x * 8u;
                         sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
                     }
@@ -464,10 +499,13 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
             const int nC = sm.n_chunks;
             uint2 A[kDepth], Bf[kDepth];
             if (nC > 0) load_chunk(sm.chunk[0].off, sm.chunk[0].len, A);
+            if (nC > 1) prefetch_chunk(1);
             for (int i = 0; i < nC; i += 2) {
+                if (i + 2 < nC) prefetch_chunk(i + 2);
                 if (i + 1 < nC) load_chunk(sm.chunk[i + 1].off, sm.chunk[i + 1].len, Bf);
                 consume(i, A);
                 if (i + 1 >= nC) break;
+                if (i + 3 < nC) prefetch_chunk(i + 3);
                 if (i + 2 < nC) load_chunk(sm.chunk[i + 2].off, sm.chunk[i + 2].len, A);
                 consume(i + 1, Bf);
             }
@@ -704,7 +742,7 @@ static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const do
         // queries per work item: as many as possible (<= kMaxQpc) while there are a few items per group
         const int sms = hs_num_sms(idx->device);
         int qpc = B < kMaxQpc ? B : kMaxQpc;
-        while (qpc > 1 && (int64_t)p.n_tiles * ((B + qpc - 1) / qpc) < (int64_t)8 * kGroups * sms) qpc = (qpc + 1) / 2;
+        while (qpc > 1 && (int64_t)p.n_tiles * ((B + qpc - 1) / qpc) < (int64_t)16 * kGroups * sms) qpc = qpc / 2;
         const int nqg = (B + qpc - 1) / qpc;
         const int64_t n_items = (int64_t)p.n_tiles * nqg;
         const int64_t rows = p.impact_table != nullptr ? (int64_t)p.max_dl + 1 : 0;
