@@ -260,8 +260,8 @@ struct __align__(16) ChunkDesc {
 };
 
 struct BatchSmem {
-    double acc[kTileDocs];
-    uint32_t row[kTileDocs];                   // TABLE: dl * (tf_cap + 1), else dl
+    double acc[kTileDocs + 2];                 // + a dummy slot that absorbs the padding of partial chunks
+    uint32_t row[kTileDocs + 4];               // what the impact lookup needs per doc (see frac_fast)
     ChunkDesc chunk[2 * kTokWindow];           // a slice holds <= kTileDocs = 2 * kChunkB postings
     double idf[kTokWindow];
     int qoff[kMaxQpc + 1];
@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
                 const uint32_t dl = p.dl[d_lo + j];
                 sm.row[j] = MODE == 2 ? tbl_s + dl * stride * 8u : (MODE == 1 ? dl * stride : dl);
             }
+            if (tid == 0) sm.row[kTileDocs] = MODE == 2 ? tbl_s : 0u;      // dummy doc: length 0
             staged_tile = tile;
         }
         if (tid <= nb) sm.qoff[tid] = p.q_off[b0 + tid];
@@ -386,9 +387,9 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
             } else if (len <= kBThreads) {
                 if (tid < len) buf[0] = __ldg(pp);
             } else {
+                const uint2 pad = make_uint2((uint32_t)d_lo + kTileDocs, 0u);           // dummy doc, tf = 0
 #pragma unroll
-                for (int u = 0; u < kDepth; ++u)
-                    if (tid + u * kBThreads < len) buf[u] = __ldg(pp + u * kBThreads);
+                for (int u = 0; u < kDepth; ++u) buf[u] = (tid + u * kBThreads < len) ? __ldg(pp + u * kBThreads) : pad;
             }
         };
         // r: what sm.row holds for the doc (MODE 2: shared-memory address of its table row, MODE 1: row index
@@ -420,46 +421,38 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
                 ++bq;
             }
             const double idf = sm.idf[d.tok];
-            if (d.len == kChunkB) {
-                // one test per thread instead of one per posting: the OR of the tfs bounds their maximum
+            if (d.len > kBThreads) {
+                // full chunks and padded partial ones share this path: no per-posting predicates; one slow-path
+                // test per thread (the OR of the tfs bounds their maximum)
                 uint32_t tf_or = 0;
 #pragma unroll
                 for (int u = 0; u < kDepth; ++u) tf_or |= buf[u].y;
                 const bool fast = MODE != 0 && tf_or <= p.tf_cap;
 #pragma unroll
                 for (int h = 0; h < kDepth; h += 4) {
-                    double fr[4], cur[4];
-                    uint32_t r[4];
+                    if (h * kBThreads < d.len) {                                     // group-uniform
+                        double fr[4], cur[4];
+                        uint32_t r[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) r[u] = lds_u32(row_s + buf[h + u].x * 4u);
-                    if (fast) {
+                        for (int u = 0; u < 4; ++u) r[u] = lds_u32(row_s + buf[h + u].x * 4u);
+                        if (fast) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) fr[u] = frac_fast(r[u], buf[h + u].y);
-                    } else {
+                            for (int u = 0; u < 4; ++u) fr[u] = frac_fast(r[u], buf[h + u].y);
+                        } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) fr[u] = frac_any(r[u], buf[h + u].y);
-                    }
+                            for (int u = 0; u < 4; ++u) fr[u] = frac_any(r[u], buf[h + u].y);
+                        }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) cur[u] = lds_f64(acc_s + buf[h + u].x * 8u);
+                        for (int u = 0; u < 4; ++u) cur[u] = lds_f64(acc_s + buf[h + u].x * 8u);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        sts_f64(acc_s + buf[h + u].x * 8u, __dadd_rn(cur[u], __dmul_rn(idf, fr[u])));
-                }
-            } else if (d.len <= kBThreads) {
-                if (tid < d.len) {
-                    const double f = frac_any(lds_u32(row_s + buf[0].x * 4u), buf[0].y);
-                    const uint32_t a = acc_s + buf[0].x * 8u;
-                    sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < kDepth; ++u) {
-                    if (tid + u * kBThreads < d.len) {
-                        const double f = frac_any(lds_u32(row_s + buf[u].x * 4u), buf[u].y);
-                        const uint32_t a = acc_s + buf[u].x * 8u;
-                        sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
+                        for (int u = 0; u < 4; ++u)
+                            sts_f64(acc_s + buf[h + u].x * 8u, __dadd_rn(cur[u], __dmul_rn(idf, fr[u])));
                     }
                 }
+            } else if (tid < d.len) {
+                const double f = frac_any(lds_u32(row_s + buf[0].x * 4u), buf[0].y);
+                const uint32_t a = acc_s + buf[0].x * 8u;
+                sts_f64(a, __dadd_rn(lds_f64(a), __dmul_rn(idf, f)));
             }
             gsync();                                         // token order: these updates land before the next token's
         };
