@@ -309,7 +309,12 @@ def run_ours(args):
     host_batches = [batch_of(args.warmup + s) for s in range(args.steps)]
     barrier()
     t0 = time.perf_counter()
-    for res_sc, res_ids in eng.search_hybrid_bm25_stream(host_batches, k, 0.6, 0.4):
+    # batches in flight: 2 overlaps the upload / launch work of batch i+1 with batch i on the GPU and is what
+    # helps at 1-4 ranks (+5..12 % end to end); at 8 ranks, where a step is ~0.5 ms and two NCCL collectives
+    # per step tie the ranks together, the overlapped loop measured slower (8.8 k vs 11.3 k q/s), so each result
+    # is handed over before the next batch is launched there
+    depth = 2 if world <= 4 else 1
+    for res_sc, res_ids in eng.search_hybrid_bm25_stream(host_batches, k, 0.6, 0.4, depth=depth):
         pass                                        # device -> host read of every step's result
     res_ids = torch.from_numpy(res_ids)
     barrier()
@@ -353,7 +358,7 @@ def run_ours(args):
                        "queries_per_step": B, "dense_mode": args.dense_mode, "parallelism": f"doc-shard x{world}",
                        "l2": "inputs larger than L2 (corpus pass 15.4 GB/step per shard set)",
                        "index_build_s": round(build_s, 1)},
-            "e2e": {"value": args.steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": args.steps * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "batches_in_flight": depth,
                     "d2h_bytes_per_step": d2h, "same_ids_as_device_run": same},
             "parity": {"topk_ids_equal_to_exact_mode": ids_equal_exact,
                        "note": "exact mode == CPU oracle bit for bit (tests/test_gpu_parity.py)"},
