@@ -2,8 +2,10 @@
 // BM25.score / score_batch, called from pipelines.py:271,328,485).
 //
 // Design (doc-range tiles, no global atomics, no score buffer round trip through HBM during
-// accumulation):
-//   * grid = (doc tiles, queries).  A CTA owns kTileDocs consecutive docs and keeps their float64
+// accumulation).  Two kernels implement it -- bm25_batch_kernel (default: persistent, several queries per tile,
+// register-pipelined posting stream, impact table in shared memory; described where it is defined) and
+// bm25_tile_kernel (one CTA per (tile, query); kept for A/B runs, HS_BM25_IMPL=tile) -- with the same arithmetic:
+//   * a CTA (or a 256-thread group of it) owns kTileDocs consecutive docs and keeps their float64
 //     partial scores in shared memory; the tile's doc lengths are staged into shared memory once
 //     (coalesced) -- the "document-length table staged in shared memory" of the north star.
 //   * for each query token IN QUERY ORDER (bm25.py:99, duplicates included) the CTA locates the

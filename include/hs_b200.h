@@ -70,7 +70,9 @@ int hs_index_set_csr(hs_index* idx, const int64_t* indptr, const uint32_t* posti
                      int64_t n_postings);
 /* doc lengths u32[n_docs] after stop-word removal (bm25.py:59-60), corpus-global avgdl (bm25.py:71),
  * k1, b (bm25.py:19-33); impact_table double[(max_dl+1) * (tf_cap+1)] from hs_bm25_impact_table, or
- * NULL to compute every posting inline */
+ * NULL to compute every posting inline.  With a table the call checks max(dl) <= max_dl on the device
+ * (synchronous, index time) because the scoring kernels index the table by doc length unchecked; the
+ * kernels keep a copy of the table in shared memory when (max_dl+1) * ((tf_cap+1)|1) <= ~10 000 entries */
 int hs_index_set_doc_stats(hs_index* idx, const uint32_t* dl, double avgdl, double k1, double b,
                            const double* impact_table, uint32_t max_dl, uint32_t tf_cap);
 
