@@ -131,3 +131,15 @@ def test_faiss_flat_io_reproduces_the_reference_file(tmp_path):
     with pytest.raises(ValueError):
         open(path, "wb").write(b"nope" + b"\\0" * 60)
         faiss_io.read_index_flat(path)
+
+
+def test_token_hash_host_twin():
+    """index_build.py: the host twin of the device token hash is a 63-bit value, distinct for the stop words and
+    for a sample of synthetic terms (term identity of the device index build)."""
+    from hybrid_search_engine_b200.extractor import STOPWORDS
+    from hybrid_search_engine_b200.index_build import STOP_HASHES, token_hash
+    assert len(set(STOP_HASHES.tolist())) == len(STOPWORDS) == 48
+    hs_ = {token_hash(f"t{i}") for i in range(200000)} | {token_hash(w) for w in STOPWORDS}
+    assert len(hs_) == 200000 + 48 and all(0 <= h < (1 << 63) for h in hs_)
+    assert token_hash("t0") == 1444696336046087048 and token_hash("the") == 3841901135645180336   # pinned values
+    assert token_hash("ab") != token_hash("ba") and token_hash("a") != token_hash("a_")
