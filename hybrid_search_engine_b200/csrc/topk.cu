@@ -22,6 +22,8 @@
 
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -318,9 +320,9 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
     bool redo = (t0 == 0);                                   // no bound: go straight to the safe path
     if (!redo) {
         const float thr_f = hs_dec_f32((uint32_t)(t0 >> 32));
-        // warp-level pre-filter: the estimate of fuse_score_estimate as one subtract and two FMAs per element,
-        // (a - sa) * ca + ((b - sb) * cb + c0) with the margin folded into c0.  A warp whose 8 x 32 elements all
-        // stay below the bound skips the per-element path altogether (~99.9 % of the iterations).
+        // per-thread pre-filter: the estimate of fuse_score_estimate as one subtract and two FMAs per element,
+        // (a - sa) * ca + ((b - sb) * cb + c0) with the margin folded into c0.  A thread whose 8 elements all
+        // stay below the bound (all but ~0.6 % of them) does nothing else in the iteration.
         float sa = 0.f, ca = 1.f, sb = 0.f, cb = 0.f, c0 = 0.f;
         if (p.mode != HS_FUSE_RAW) {
             sa = c.const_a ? 0.f : c.min_a;
@@ -375,12 +377,21 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
                     for (int e = 0; e < 4; ++e)
                         cand |= !(__fmaf_rn(__fsub_rn(ax[e], sa), ca, __fmaf_rn(__fsub_rn(bx[e], sb), cb, c0)) < thr_f);
                 }
-                if (!__any_sync(0xFFFFFFFFu, cand)) continue;
+                if (!cand) continue;
+                // rare (about one thread in a thousand): exact keys of this thread's survivors, appended one by one
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
                     const float ax[4] = {a4[v].x, a4[v].y, a4[v].z, a4[v].w}, bx[4] = {b4[v].x, b4[v].y, b4[v].z, b4[v].w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) consider(ax[e], bx[e], base + v * (kThreads * 4) + tid * 4 + e, true);
+                    for (int e = 0; e < 4; ++e) {
+                        if (__fmaf_rn(__fsub_rn(ax[e], sa), ca, __fmaf_rn(__fsub_rn(bx[e], sb), cb, c0)) < thr_f) continue;
+                        const int64_t i = base + v * (kThreads * 4) + tid * 4 + e;
+                        const uint64_t kk = hs_make_key(fuse_score(p, c, ax[e], bx[e]), (uint32_t)(p.doc_base + i));
+                        if (kk >= below || kk <= t0) continue;
+                        const int pos = atomicAdd(&sel.cnt, 1);
+                        if (pos < CAP) sel.buf[pos] = kk;
+                        else overflow = 1;
+                    }
                 }
             } else {                                            // unaligned rows and the ragged tail
                 for (int64_t i0 = base + tid; i0 < base + kStep; i0 += kThreads) {
