@@ -70,7 +70,10 @@ class SearchEngine:
         key = f"pin{self._pin_slot}_{name}"
         t = self._bufs.get(key)
         if t is None or t.numel() < need or t.dtype != dtype:
-            t = torch.empty(max(need, 1), dtype=dtype, pin_memory=True)
+            # page-locked allocations are slow and synchronise the device: round the capacity up generously so
+            # that a batch with a few more tokens than the last one never triggers one in a serving loop
+            cap = max(1024, 1 << (max(need, 1) - 1).bit_length())
+            t = torch.empty(cap, dtype=dtype, pin_memory=True)
             self._bufs[key] = t
         return t[:need].view(*shape)
 
