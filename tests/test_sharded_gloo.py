@@ -1,4 +1,4 @@
-"""N > 1 host logic on CPU: world_size-2 gloo run of the doc-sharded exchange (C2 stats all-reduce,
+"""N > 1 host logic on CPU: world_size-2 and -3 gloo runs of the doc-sharded exchange (C2 stats all-reduce,
 C1 key all-gather + merge) around per-shard scores computed by the oracle.  The sharded result must
 equal the unsharded oracle bit for bit (SURVEY.md section 8e "exactness under sharding")."""
 import os
@@ -56,17 +56,21 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_equals_unsharded(tmp_path):
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_equals_unsharded(tmp_path, world):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     spec = synth.SynthSpec(n_docs=1501, vocab=400, dim=48, min_len=3, max_len=30)
     docs = synth.doc_texts(spec, 0, spec.n_docs)
     ix = orc.build_index(docs, synth.embeddings(spec, 0, spec.n_docs))
     queries = synth.query_texts(spec, 0, 5)
     qv = synth.query_embeddings(spec, 0, 5)
-    r0, r1 = (np.load(tmp_path / f"rank{r}.npz") for r in range(world))
-    assert (int(r0["lo"]), int(r0["hi"]), int(r1["lo"]), int(r1["hi"])) == (0, 751, 751, 1501)
-    assert np.array_equal(r0["ids"], r1["ids"]) and np.array_equal(r0["sc"], r1["sc"])   # every rank: same result
+    res = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    r0 = res[0]
+    assert [(int(r["lo"]), int(r["hi"])) for r in res] == [parallel.shard_bounds(1501, world, r) for r in range(world)]
+    if world == 2:
+        assert (int(res[1]["lo"]), int(res[1]["hi"])) == (751, 1501)
+    for r in res[1:]:                                                             # every rank: same result
+        assert np.array_equal(r0["ids"], r["ids"]) and np.array_equal(r0["sc"], r["sc"])
     for b, q in enumerate(queries):
         ids, sc, _ = orc.search_hybrid_bm25(ix, q, qv[b], 37)
         assert np.array_equal(r0["ids"][b], ids)
