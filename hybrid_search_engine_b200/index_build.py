@@ -49,11 +49,14 @@ class DeviceLexicalStats:
         self.device = torch.device(device)
         self.remove_stopwords = remove_stopwords
         self.lib = _lib.load()
+        self._documents = None
+        self._vocab = None
 
     def fit(self, documents: Sequence[str], chunk_bytes: int = 1 << 28):
         dev, lib = self.device, self.lib
         n = len(documents)
         self.doc_count = n
+        self._documents, self._vocab = documents, None      # only for the lazy `vocab` property
         hashes: List[torch.Tensor] = []
         docs_of: List[torch.Tensor] = []
         start = 0
@@ -114,6 +117,24 @@ class DeviceLexicalStats:
             self.vocab_hashes = uniq.cpu().numpy()
             self.max_dl = int(dl.max().item()) if n else 0
         return self
+
+    @property
+    def vocab(self):
+        """term string -> term id, as ``LexicalStats.vocab`` -- built on first use by tokenising the documents on
+        the host (slow; the device build itself never needs the strings).  Also the place where a collision of the
+        63-bit term hash would surface: two different strings with one id raise."""
+        if self._vocab is None:
+            vh, out, owner = self.vocab_hashes, {}, {}
+            for doc in self._documents or ():
+                for t in extract_tokens(doc, remove_stopwords=self.remove_stopwords):
+                    if t in out:
+                        continue
+                    i = int(np.searchsorted(vh, token_hash(t)))
+                    if owner.setdefault(i, t) != t:
+                        raise RuntimeError(f"term hash collision between {owner[i]!r} and {t!r}")
+                    out[t] = i
+            self._vocab = out
+        return self._vocab
 
     def query_term_ids(self, query: str) -> List[int]:
         """bm25.py:94,99-101 -- query tokens in order, duplicates kept, unknown terms dropped."""
