@@ -290,7 +290,7 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v) {
 // tag lookup per cache line (32 cycles per warp instruction, which made mode 1 L1-bound at ~0.35 of the HBM
 // peak) but only ~5 bank-conflict wavefronts in shared memory -- mode 2 is the default whenever the table fits.
 // The kernel is persistent, one CTA per SM: kGroups independent 256-thread groups (named barriers), each with
-// its own tile buffers, share the one table copy and pull (tile, query group) work items round-robin.
+// its own tile buffers, share the one table copy; each takes a contiguous run of (tile, query group) work items.
 constexpr int kGroups = 3;
 
 template <int MODE>
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
             s_table[r * stride + c] = p.impact_table[i];
         }
     }
-    for (int j = tid; j < kTileDocs; j += kBThreads) sm.acc[j] = 0.0;
+    for (int j = tid; j < kTileDocs + 2; j += kBThreads) sm.acc[j] = 0.0;      // incl. the dummy slot
     __syncthreads();
     auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kBThreads) : "memory"); };
     const uint32_t tbl_s = (uint32_t)__cvta_generic_to_shared(s_table);
@@ -394,20 +394,20 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
                 for (int u = 0; u < kDepth; ++u) buf[u] = (tid + u * kBThreads < len) ? __ldg(pp + u * kBThreads) : pad;
             }
         };
-        // r: what sm.row holds for the doc (MODE 2: shared-memory address of its table row, MODE 1: row index
-        // times the row stride, MODE 0: the doc length)
-        // one thread asks the L2 for the chunk after next (16-byte aligned range inside the slice), so that the
+        // one thread asks the L2 for the chunk after next (the 16-byte aligned part of its byte range), so that the
         // register loads issued one chunk ahead find their lines on chip
         auto prefetch_chunk = [&](int ci) {
             if (tid == 0) {
                 const ChunkDesc d = sm.chunk[ci];
-                const int64_t lo = (d.off + 1) & ~(int64_t)1, hi = (d.off + d.len) & ~(int64_t)1;
+                const uintptr_t lo = (reinterpret_cast<uintptr_t>(p.postings + d.off) + 15) & ~(uintptr_t)15;
+                const uintptr_t hi = reinterpret_cast<uintptr_t>(p.postings + d.off + d.len) & ~(uintptr_t)15;
                 if (hi > lo)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.postings + lo),
-                                 "r"((uint32_t)(hi - lo) * 8u)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo))
                                  : "memory");
             }
         };
+        // r: what sm.row holds for the doc (MODE 2: shared-memory address of its table row, MODE 1: row index
+        // times the row stride, MODE 0: the doc length)
         auto frac_fast = [&](uint32_t r, uint32_t tf) -> double {                 // requires tf <= tf_cap
             return MODE == 2 ? lds_f64(r + tf * 8u) : __ldg(p.impact_table + (r + tf));
         };
