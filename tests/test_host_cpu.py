@@ -143,3 +143,23 @@ def test_token_hash_host_twin():
     assert len(hs_) == 200000 + 48 and all(0 <= h < (1 << 63) for h in hs_)
     assert token_hash("t0") == 1444696336046087048 and token_hash("the") == 3841901135645180336   # pinned values
     assert token_hash("ab") != token_hash("ba") and token_hash("a") != token_hash("a_")
+
+
+def test_doc_table_reranker_and_weight_validation():
+    """Host-only pieces of core.py: the two-column doc table (core.py:240-241 of the reference), the injectable
+    stage-3 reranker (reranker.py:50-89: stable sort by the external score, optional cut) and the weight check
+    of Searcher.search (core.py:232-233), which fires before any device work."""
+    from hybrid_search_engine_b200.core import CrossEncoderReranker, DocTable, Searcher
+    t = DocTable(["a b", "c", ""])
+    assert len(t) == 3 and t["content"].to_list() == ["a b", "c", ""] and t["doc_id"].to_list() == [0, 1, 2]
+    assert t["content"][1] == "c" and len(t["doc_id"]) == 3
+    with pytest.raises(KeyError):
+        t["nope"]
+    rr = CrossEncoderReranker(predict=lambda pairs: [len(c) for _, c in pairs])
+    res = [(0.9, "x", 0), (0.8, "yyy", 1), (0.7, "zz", 2), (0.6, "ww", 3)]
+    assert rr.rerank("q", res) == [(3.0, "yyy", 1), (2.0, "zz", 2), (2.0, "ww", 3), (1.0, "x", 0)]    # ties keep order
+    assert rr.rerank("q", res, top_k=2) == [(3.0, "yyy", 1), (2.0, "zz", 2)]
+    assert rr.rerank("q", []) == []
+    s = Searcher(encoder=object())
+    with pytest.raises(ValueError, match="semantic_weight and lexical_weight must sum to 1.0"):
+        s.search("q", DocTable(["a"]), np.ones((1, 4), np.float32), semantic_weight=0.5, lexical_weight=0.6)
