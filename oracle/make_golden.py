@@ -196,3 +196,58 @@ def main_plus():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "plus":
     main_plus()
+
+
+T2_SPEC = dict(n_docs=60_000, vocab=100_000, dim=128)
+T2_EXTRA_QUERIES = ["t5 t5 t9", "unknownterm t1"]
+
+
+def main_t2():
+    """T2 tier: the unmodified reference at a size where BM25 spans many doc tiles
+    (60 k docs x 100-300 tokens, 100 k-term Zipf vocabulary, 128-d).  Full score vectors are too large to commit,
+    so the fixture keeps the reference's top-100 of hybrid_bm25, the canonical top-100 of its BM25 vector, a
+    sha256 of the whole BM25 vector (the oracle reproduces it bit for bit) and the reference cosine at 2048
+    sampled docs -> tests/golden/t2_60k.npz (+ .json).   python -m oracle.make_golden t2"""
+    import hashlib
+    ref = refload.load()
+    spec = synth.SynthSpec(**T2_SPEC)
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    docs = synth.doc_texts(spec, 0, spec.n_docs, th)
+    emb = synth.embeddings(spec, 0, spec.n_docs)
+    queries = synth.query_texts(spec, 0, 6, th) + T2_EXTRA_QUERIES
+    q_emb = synth.query_embeddings(spec, 0, len(queries))
+    refload.EMBED_DIM[0] = emb.shape[1]
+    refload.EMBED_TABLE.clear()
+    for t, e in list(zip(map(orc.preprocess_text, docs), emb)) + list(zip(queries, q_emb)):
+        assert t not in refload.EMBED_TABLE or np.array_equal(refload.EMBED_TABLE[t], e), t[:40]
+        refload.EMBED_TABLE[t] = e
+    refload.PARTIAL_RATIO_FN[0] = lambda a, b: 50.0        # lexical weight is 0.0 on this path
+    hyb = ref.pipelines.create_pipeline("hybrid_bm25")
+    hyb.index(docs)
+    assert np.array_equal(hyb.vectors, emb)
+    out = {"doc_lengths_sha256": np.array(hashlib.sha256(np.asarray(hyb.bm25.doc_lengths, np.int64).tobytes()).hexdigest()),
+           "avg_doc_len": np.float64(hyb.bm25.avg_doc_len),
+           "cos_sample_idx": np.sort(np.random.default_rng(5).choice(spec.n_docs, 2048, replace=False))}
+    for qi, (q, qe) in enumerate(zip(queries, q_emb)):
+        k = f"q{qi}_"
+        bm = hyb.bm25.score_batch(q)
+        out[k + "bm25_sha256"] = np.array(hashlib.sha256(np.ascontiguousarray(bm).tobytes()).hexdigest())
+        top = orc.canonical_topk(bm, 100)
+        out[k + "bm25_top_ids"], out[k + "bm25_top_scores"] = top.astype(np.int64), bm[top]
+        cos = ref.utils.batch_cosine_sim(qe.astype(np.float32), hyb.vectors)
+        out[k + "cos_sample"] = cos[out["cos_sample_idx"]]
+        r = hyb.search(q, top_k=100)
+        out[k + "hyb_ids"] = np.array([x["doc_id"] for x in r.results], np.int64)
+        out[k + "hyb_scores"] = np.array([x["score"] for x in r.results], np.float32)
+        out[k + "cos_at_hyb"] = cos[out[k + "hyb_ids"]]
+        out[k + "bm25_at_hyb"] = bm[out[k + "hyb_ids"]]
+        out[k + "cos_minmax"] = np.array([cos.min(), cos.max()], np.float32)
+        out[k + "bm25_max"] = np.float32(bm.max())
+        print("t2 query", qi, repr(q), "done", flush=True)
+    np.savez_compressed(os.path.join(GOLDEN, "t2_60k.npz"), **out)
+    json.dump({"spec": T2_SPEC, "queries": queries}, open(os.path.join(GOLDEN, "t2_60k.json"), "w"), indent=1)
+    print("t2 golden written")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "t2":
+    main_t2()

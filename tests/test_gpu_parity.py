@@ -607,3 +607,38 @@ def test_bm25_batched_kernel_shapes(hs, max_len, tf_hi):
     f = torch.empty((len(queries), 4), dtype=torch.float32, device="cuda:0")
     check(load().hs_stats_decode(ptr(stats), ptr(f), len(queries), stream_ptr(f.device)))
     assert np.array_equal(f.cpu().numpy()[:, 2], want.astype(np.float32).max(axis=1))      # HS_STAT_MAX_B
+
+
+def test_t2_reference_at_60k_docs(hs):
+    """T2 tier: the CUDA path against outputs of the unmodified reference on a 60 k-doc corpus (15 doc tiles;
+    index built on the device): the whole BM25 vector bit for bit (sha256), the bm25 pipeline's top-100, and the
+    hybrid_bm25 top-100 (ids up to near ties of the fused score -- the reference's cosine has no defined
+    summation order -- scores within the 1e-5 relative tolerance)."""
+    import hashlib
+    from tests.golden_cases import load_t2
+    c = load_t2()
+    p = hs.create_pipeline("hybrid_bm25", index_build="device")
+    p.index(c.docs, embeddings=c.emb)
+    assert hashlib.sha256(np.asarray(p.bm25.doc_lengths, np.int64).tobytes()).hexdigest() == str(c.ref["doc_lengths_sha256"])
+    assert float(p.bm25.avg_doc_len) == float(c.ref["avg_doc_len"])
+    bm = p.bm25.score_batch_many(c.queries)
+    res = p.search_many(c.queries, top_k=100, query_vectors=c.q_emb)
+    b = hs.create_pipeline("bm25", index_build="device")
+    b.index(c.docs)
+    bres = b.search_many(c.queries, top_k=100)
+    for qi, q in enumerate(c.queries):
+        assert hashlib.sha256(np.ascontiguousarray(bm[qi]).tobytes()).hexdigest() == str(c.ref[f"q{qi}_bm25_sha256"]), q
+        assert [x["doc_id"] for x in bres[qi].results] == c.ref[f"q{qi}_bm25_top_ids"].tolist()
+        assert [x["score"] for x in bres[qi].results] == [float(s) for s in c.ref[f"q{qi}_bm25_top_scores"]]
+        ids = np.array([x["doc_id"] for x in res[qi].results])
+        sc = np.array([x["score"] for x in res[qi].results], np.float32)
+        ref_ids, ref_sc = c.ref[f"q{qi}_hyb_ids"], c.ref[f"q{qi}_hyb_scores"]
+        score_of = dict(zip(ids.tolist(), sc.tolist()))
+        score_of.update(zip(ref_ids.tolist(), ref_sc.tolist()))
+        for a, r in zip(ids, ref_ids):
+            assert a == r or abs(score_of[int(a)] - score_of[int(r)]) <= 2e-6, (q, a, r)
+        common = np.intersect1d(ids, ref_ids)
+        assert len(common) >= 98
+        mine = dict(zip(ids.tolist(), sc.tolist()))
+        theirs = dict(zip(ref_ids.tolist(), ref_sc.tolist()))
+        np.testing.assert_allclose([mine[int(d)] for d in common], [theirs[int(d)] for d in common], rtol=1e-5, atol=1e-6)

@@ -156,3 +156,29 @@ def test_edge_cases():
         orc.searcher_hybrid(np.ones(3, np.float32), np.ones(3, np.float32), 0.7, 0.2)
     # top_k > N returns N
     assert len(orc.canonical_topk(np.array([0.1, 0.5], np.float32), 10)) == 2
+
+
+def test_t2_reference_at_60k_docs():
+    """T2 tier: the oracle against the unmodified reference on a 60 k-doc corpus (BM25 posting lists spanning many
+    doc tiles).  The BM25 vector is compared through its sha256 (bit-exact), the cosine at 2048 sampled docs
+    (4 ulp), the hybrid top-100 by ids (up to near ties) and scores."""
+    import hashlib
+    from tests.golden_cases import load_t2
+    c = load_t2()
+    ix = orc.build_index(c.docs, c.emb)
+    assert hashlib.sha256(np.asarray(ix.bm25.doc_lengths, np.int64).tobytes()).hexdigest() == str(c.ref["doc_lengths_sha256"])
+    assert float(ix.bm25.avg_doc_len) == float(c.ref["avg_doc_len"])
+    idx = c.ref["cos_sample_idx"]
+    for qi, q in enumerate(c.queries):
+        bm = orc.bm25_score_batch(ix.bm25, q)
+        assert hashlib.sha256(np.ascontiguousarray(bm).tobytes()).hexdigest() == str(c.ref[f"q{qi}_bm25_sha256"]), q
+        top = orc.canonical_topk(bm, 100)
+        assert np.array_equal(top, c.ref[f"q{qi}_bm25_top_ids"]) and np.array_equal(bm[top], c.ref[f"q{qi}_bm25_top_scores"])
+        cos = orc.cosine_exact(c.q_emb[qi], c.emb, ix.vnorm)
+        assert np.max(np.abs(cos[idx].astype(np.float64) - c.ref[f"q{qi}_cos_sample"])) <= COS_ATOL
+        ids, sc, fused = orc.search_hybrid_bm25(ix, q, c.q_emb[qi], 100)
+        ref_ids, ref_sc = c.ref[f"q{qi}_hyb_ids"], c.ref[f"q{qi}_hyb_scores"]
+        np.testing.assert_allclose(fused[ref_ids], ref_sc, rtol=1e-5, atol=1e-6)
+        ref_full = fused.copy()
+        ref_full[ref_ids] = ref_sc
+        assert _near_tie_equal(ids, ref_ids, ref_full, 2e-6), q
