@@ -163,3 +163,40 @@ def test_doc_table_reranker_and_weight_validation():
     s = Searcher(encoder=object())
     with pytest.raises(ValueError, match="semantic_weight and lexical_weight must sum to 1.0"):
         s.search("q", DocTable(["a"]), np.ones((1, 4), np.float32), semantic_weight=0.5, lexical_weight=0.6)
+
+
+def test_bm25_work_partition_model():
+    """Python mirror of the work partition of bm25_batch_kernel (csrc/bm25.cu: host choice of queries per item,
+    contiguous item runs per group, merging of same-tile items): every (doc tile, query) pair must be scored exactly
+    once, in passes of 1..8 queries, for awkward batch sizes and tile counts.  Keep in sync with the kernel."""
+    k_max_qpc, k_groups = 8, 3
+
+    def run(n_tiles, B, sms=148):
+        qpc = min(B, k_max_qpc)
+        while qpc > 1 and n_tiles * ((B + qpc - 1) // qpc) < 16 * k_groups * sms:
+            qpc //= 2
+        nqg = (B + qpc - 1) // qpc
+        n_items = n_tiles * nqg
+        grid = min((n_items + k_groups - 1) // k_groups, sms)
+        seen = set()
+        for me in range(grid * k_groups):
+            item, hi = n_items * me // (grid * k_groups), n_items * (me + 1) // (grid * k_groups)
+            while item < hi:
+                tile, qg = divmod(item, nqg)
+                qg_end = qg + (hi - item) if hi - item < nqg - qg else nqg
+                if (qg_end - qg) * qpc > k_max_qpc:
+                    qg_end = qg + k_max_qpc // qpc
+                b0 = qg * qpc
+                nb = min(B, qg_end * qpc) - b0
+                assert qg_end > qg and 1 <= nb <= k_max_qpc
+                for b in range(b0, b0 + nb):
+                    assert (tile, b) not in seen
+                    seen.add((tile, b))
+                item += qg_end - qg
+        assert len(seen) == n_tiles * B
+
+    for n_tiles in (1, 2, 7, 100, 305, 977, 2442):
+        for B in (1, 2, 3, 5, 7, 8, 9, 13, 19, 32, 33, 100):
+            run(n_tiles, B)
+    run(50, 19, sms=1)
+    run(50, 19, sms=132)
