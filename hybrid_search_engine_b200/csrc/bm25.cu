@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
                     sm.idf[lane] = p.q_idf[t];
                 }
                 const int len = (int)(hi - lo);                  // <= kTileDocs: a doc occurs once per posting list
-                const int n = (len + kChunkB - 1) / kChunkB;
+                const int n = (len + kChunkB - 1) / kChunkB < 2 ? (len + kChunkB - 1) / kChunkB : 2;   // chunk[] holds 2 per token
                 int incl = n;
 #pragma unroll
                 for (int dlt = 1; dlt < 32; dlt <<= 1) {
