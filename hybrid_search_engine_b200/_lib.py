@@ -13,10 +13,10 @@ import torch  # noqa: F401  (loads libcudart before our library so both share on
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhs_b200.so")
 
-HS_DENSE_EXACT, HS_DENSE_FP32, HS_DENSE_BF16 = 0, 1, 2
+HS_DENSE_EXACT, HS_DENSE_FP32, HS_DENSE_BF16, HS_DENSE_TF32X3 = 0, 1, 2, 3
 HS_FUSE_RAW, HS_FUSE_SEARCHER, HS_FUSE_HYBRID_BM25 = 0, 1, 2
 HS_TOPK_MAX = 2048
-DENSE_MODES = {"exact": HS_DENSE_EXACT, "fp32": HS_DENSE_FP32, "bf16": HS_DENSE_BF16}
+DENSE_MODES = {"exact": HS_DENSE_EXACT, "fp32": HS_DENSE_FP32, "bf16": HS_DENSE_BF16, "tf32x3": HS_DENSE_TF32X3}
 
 _vp, _i32, _i64, _u32, _u64, _f64, _sz = (C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64,
                                           C.c_double, C.c_size_t)
@@ -29,7 +29,7 @@ SIGNATURES = {
     "hs_index_destroy": (C.c_int, [_vp]),
     "hs_index_set_dense": (C.c_int, [_vp, _vp, _i32, _i64, _vp]),
     "hs_index_set_csr": (C.c_int, [_vp, _vp, _vp, _i64, _i64]),
-    "hs_index_set_doc_stats": (C.c_int, [_vp, _vp, _f64, _f64, _f64, _vp, _u32, _u32]),
+    "hs_index_set_doc_stats": (C.c_int, [_vp, _vp, _f64, _f64, _f64, _vp, _u32, _u32, _vp]),
     "hs_row_norms": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp]),
     "hs_bm25_impact_table": (C.c_int, [_f64, _f64, _f64, _u32, _u32, _vp, _vp]),
     "hs_stats_reset": (C.c_int, [_vp, _i32, _vp]),
@@ -40,12 +40,17 @@ SIGNATURES = {
     "hs_stats_fold_minmax": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
     "hs_dense_scan": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "hs_index_set_dense_bf16": (C.c_int, [_vp, _vp, _i64]),
-    "hs_dense_scan_bf16_workspace_bytes": (_sz, [_vp, _i32]),
-    "hs_dense_scan_bf16": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _sz, _vp, _vp, _vp]),
+    "hs_dense_gemm_workspace_bytes": (_sz, [_vp, _i32, _i32]),
+    "hs_dense_gemm": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i64, _vp, _sz, _vp, _i64, _vp, _vp]),
+    "hs_dense_gemm_filter": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i64, _vp, _sz, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "hs_topk_select": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _sz, _vp, _vp]),
+    "hs_keys_kth_score": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "hs_cand_select": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hs_bm25_workspace_bytes": (_sz, [_i64, _i32]),
     "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25plus_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "hs_bm25plus_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _f64, _vp, _vp]),
     "hs_fuse_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "hs_fuse_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),
     "hs_topk_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),

@@ -124,7 +124,8 @@ class BM25:
             raise IndexError("list index out of range")
         eng = self.engine
         ids = torch.tensor([[doc_idx]], dtype=torch.int64, device=eng.device)
-        return float(eng.bm25_score_docs([self.stats.query_term_ids(query)], ids).cpu()[0, 0])
+        return float(eng.bm25_score_docs([self.stats.query_term_ids(query)], ids,
+                                         plus_delta=self._plus_delta()).cpu()[0, 0])
 
     def search_many(self, queries: Sequence[str], top_k: int = 10) -> List[List[tuple]]:
         """bm25.py:129-142 per query -> [(doc_idx, score)], canonical order (score desc, doc_idx asc)."""
@@ -135,7 +136,7 @@ class BM25:
         if k == 0:
             return [[] for _ in queries]
         qb = QueryBatch(term_ids=[self.stats.query_term_ids(q) for q in queries])
-        sc, ids = self.engine.search_bm25(qb, k)
+        sc, ids = self.engine.search_bm25(qb, k, plus_delta=self._plus_delta())
         sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
         return [[(int(i), float(s)) for s, i in zip(sc[q], ids[q]) if i >= 0] for q in range(len(queries))]
 
@@ -150,8 +151,8 @@ class BM25Okapi(BM25):
 
 class BM25Plus(BM25):
     """bm25.py:150-179 -- adds ``delta`` inside the idf product, for every doc and every known query token
-    (tf = 0 included), so scores are dense.  ``score_batch`` runs the dense tile kernel; ``search`` /
-    ``score`` go through it as well (used by no pipeline in the reference)."""
+    (tf = 0 included), so scores are dense.  ``score_batch`` / ``search`` run the dense tile kernel (+ the device
+    top-k select), ``score`` the float64 per-doc kernel (used by no pipeline in the reference)."""
 
     def __init__(self, k1: float = 1.5, b: float = 0.75, delta: float = 1.0, **kwargs):
         super().__init__(k1=k1, b=b, **kwargs)
@@ -162,15 +163,5 @@ class BM25Plus(BM25):
     def _plus_delta(self):
         return self.delta
 
-    def score(self, query: str, doc_idx: int) -> float:
-        raise NotImplementedError("BM25Plus.score for a single doc: use score_batch(query)[doc_idx] "
-                                  "(float32) -- the float64 per-doc path is only built for Okapi")
-
-    def search_many(self, queries, top_k: int = 10):
-        scores = self.score_batch_many(queries)
-        out = []
-        for row in scores:
-            k = min(int(top_k), len(row))
-            order = np.lexsort((np.arange(len(row)), -row.astype(np.float64)))[:k]
-            out.append([(int(i), float(row[i])) for i in order])
-        return out
+    # score (float64, hs_bm25plus_score_docs) and search_many (dense tile kernel + device top-k select) are the
+    # base-class methods: _plus_delta() switches every kernel call to the BM25+ formula

@@ -109,13 +109,19 @@ class Searcher:
         self.shard: Optional[DeviceIndex] = None
         self.engine: Optional[SearchEngine] = None
         self._attached = None
+        self._doc_lists = None
 
     # ------------------------------------------------------------------
-    def attach(self, docs_df, vectors: np.ndarray):
+    def attach(self, docs_df, vectors: np.ndarray, *, force: bool = False):
         """Upload ``vectors`` (float32 [N, d], indexer.py:285) once; later searches reuse the shard."""
-        key = (id(docs_df), id(vectors), getattr(vectors, "shape", None))
-        if self._attached == key:
+        # the cache holds strong references and compares by identity: a recycled id() of a freed array can never
+        # alias it.  In-place edits of an attached array are not seen -- call attach(..., force=True) (the
+        # reference re-reads `vectors` on every search; here it lives in HBM)
+        if (not force and self._attached is not None and self._attached[0] is docs_df
+                and self._attached[1] is vectors):
             return
+        key = (docs_df, vectors)
+        self._doc_lists = None
         if not torch.cuda.is_available():
             raise _lib.HsError("no CUDA device: the hybrid scoring path has no CPU fallback")
         dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -155,8 +161,10 @@ class Searcher:
                 self._faiss_rows, _ = read_index_flat(self.faiss_index_path)
         use_faiss = self.use_faiss and self._faiss_rows is not None
         self.attach(docs_df, self._faiss_rows if use_faiss else vectors)
-        docs = docs_df["content"].to_list()
-        doc_ids = docs_df["doc_id"].to_list()
+        # column lists are materialised once per docs_df object (they also key the lexical scorer's device copy)
+        if self._doc_lists is None or self._doc_lists[0] is not docs_df:
+            self._doc_lists = (docs_df, docs_df["content"].to_list(), docs_df["doc_id"].to_list())
+        _, docs, doc_ids = self._doc_lists
         n = len(docs)
         if n == 0:
             # utils.py:67 on an empty array
@@ -173,14 +181,14 @@ class Searcher:
         if use_faiss:
             lex = None
             if lexical_weight != 0.0:
-                lex = self._lexical_scorer_obj().scores_device(query, getattr(docs_df, "contents", docs))[None, :]
+                lex = self._lexical_scorer_obj().scores_device(query, docs)[None, :]
             sc, ids = eng.search_faiss_style(QueryBatch(vectors=q), lex, k, semantic_weight, lexical_weight)
         elif lexical_weight == 0.0:
             # lex_norm * 0.0 == +0.0 for every finite lexical vector (core.py:268): skip computing it
             sc, ids = eng.search_semantic(QueryBatch(vectors=q), k, semantic_weight)
         else:
             # device-resident lexical vector; the stored list object keys the scorer's cache
-            lex = self._lexical_scorer_obj().scores_device(query, getattr(docs_df, "contents", docs))
+            lex = self._lexical_scorer_obj().scores_device(query, docs)
             sc, ids = eng.search_searcher(QueryBatch(vectors=q), lex[None, :], k, semantic_weight, lexical_weight)
         sc, ids = sc.cpu().numpy()[0], ids.cpu().numpy()[0]
         return [(float(s), docs[int(i)], doc_ids[int(i)]) for s, i in zip(sc, ids) if i >= 0]

@@ -62,6 +62,7 @@ int hs_index_set_dense(hs_index* idx, const float* vectors, int32_t dim, int64_t
     idx->vnorm = vnorm;
     idx->dim = dim;
     idx->ld = ld;
+    hs_gemm_attach_f32(idx);
     return HS_OK;
 }
 
@@ -80,21 +81,23 @@ int hs_index_set_csr(hs_index* idx, const int64_t* indptr, const uint32_t* posti
 }
 
 int hs_index_set_doc_stats(hs_index* idx, const uint32_t* dl, double avgdl, double k1, double b,
-                           const double* impact_table, uint32_t max_dl, uint32_t tf_cap) {
+                           const double* impact_table, uint32_t max_dl, uint32_t tf_cap, void* stream) {
     HS_REQUIRE(idx != nullptr, "hs_index_set_doc_stats: idx is null");
     HS_REQUIRE(dl != nullptr || idx->n_docs == 0, "hs_index_set_doc_stats: dl is null");
     if (impact_table != nullptr && idx->n_docs > 0) {
         // the scoring kernels index the table by doc length without a bound check: verify the bound once here
-        // (index time, synchronous)
+        // (index time; ordered on the caller's stream -- the one `dl` was produced on -- then synchronised)
+        cudaStream_t st = (cudaStream_t)stream;
         uint32_t* d_max = nullptr;
         uint32_t h_max = 0;
         HS_CUDA(cudaSetDevice(idx->device));
         HS_CUDA(cudaMalloc(&d_max, sizeof(uint32_t)));
-        cudaError_t e = cudaMemset(d_max, 0, sizeof(uint32_t));
+        cudaError_t e = cudaMemsetAsync(d_max, 0, sizeof(uint32_t), st);
         if (e == cudaSuccess) {
-            u32_max_kernel<<<1024, 256>>>(dl, idx->n_docs, d_max);
-            e = cudaMemcpy(&h_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+            u32_max_kernel<<<1024, 256, 0, st>>>(dl, idx->n_docs, d_max);
+            e = cudaMemcpyAsync(&h_max, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         cudaFree(d_max);
         HS_CUDA(e);
         HS_REQUIRE(h_max <= max_dl, "hs_index_set_doc_stats: a doc length (%u) exceeds max_dl (%u)", h_max, max_dl);

@@ -610,6 +610,8 @@ __global__ void impact_table_kernel(double avgdl, double k1, double one_minus_b,
 
 // BM25.score for selected docs (multi_stage stage 2, pipelines.py:485): one warp per (query, candidate);
 // per token a 32-ary search of the posting list for the doc, float64 accumulation in query order.
+// PLUS: BM25Plus.score (bm25.py:161-179) -- idf * (num / den + delta) for every known query token, tf = 0 included.
+template <bool PLUS>
 __global__ void bm25_docs_kernel(const Bm25Params p, const int64_t* __restrict__ doc_ids, int C,
                                  double* __restrict__ out, int B) {
     const int lane = threadIdx.x & 31;
@@ -625,11 +627,18 @@ __global__ void bm25_docs_kernel(const Bm25Params p, const int64_t* __restrict__
             if (term < 0 || term >= p.n_terms) continue;
             const int64_t pl = p.indptr[term], ph = p.indptr[term + 1];
             const int64_t pos = warp_lower_bound(p.postings, pl, ph, (uint32_t)doc, lane);
+            bool hit = false;
             if (pos < ph) {
                 const uint2 pt = __ldg(&p.postings[pos]);
-                if (pt.x == (uint32_t)doc)
-                    score = __dadd_rn(score, __dmul_rn(p.q_idf[t], bm25_frac(p, pt.y, dl)));
+                if (pt.x == (uint32_t)doc) {
+                    hit = true;
+                    const double frac = bm25_frac(p, pt.y, dl);
+                    score = __dadd_rn(score, __dmul_rn(p.q_idf[t], PLUS ? __dadd_rn(frac, p.delta) : frac));
+                }
             }
+            // tf = 0: numerator 0, denominator k1 * (...) -- contributes idf * (0.0 + delta) where it is > 0
+            if (PLUS && !hit && p.k1 > 0.0 && !(p.b == 1.0 && dl == 0))
+                score = __dadd_rn(score, __dmul_rn(p.q_idf[t], __dadd_rn(0.0, p.delta)));
         }
     }
     if (lane == 0) out[w] = score;
@@ -731,11 +740,12 @@ static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const do
                    "hs_bm25plus_score: needs k1 >= 0, 0 <= b <= 1 and a non-empty corpus");
         p.delta = delta;
         const size_t smem = (size_t)kTileDocs * (2 * sizeof(double) + sizeof(uint32_t));
-        HS_CUDA(cudaFuncSetAttribute(bm25plus_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t smem_set[16] = {0};
+        HS_CUDA(hs_smem_limit(bm25plus_tile_kernel, smem, smem_set));
         bm25plus_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     } else if (bm25_use_batch()) {
         // queries per work item: as many as possible (<= kMaxQpc) while there are a few items per group
-        const int sms = hs_num_sms(idx->device);
+        const int sms = idx->num_sms;
         int qpc = B < kMaxQpc ? B : kMaxQpc;
         while (qpc > 1 && (int64_t)p.n_tiles * ((B + qpc - 1) / qpc) < (int64_t)16 * kGroups * sms) qpc = qpc / 2;
         const int nqg = (B + qpc - 1) / qpc;
@@ -746,8 +756,9 @@ static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const do
         const int mode = bm25_table_mode(p.impact_table != nullptr, base + tbl_bytes);
         const size_t smem = base + (mode == 2 ? tbl_bytes : 0);
         const unsigned grid = (unsigned)((n_items + kGroups - 1) / kGroups < sms ? (n_items + kGroups - 1) / kGroups : sms);
+        static size_t smem_set[3][16] = {{0}};
         auto launch = [&](auto kern) -> int {
-            HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            HS_CUDA(hs_smem_limit(kern, smem, smem_set[mode]));
             kern<<<grid, kBThreads * kGroups, smem, (cudaStream_t)stream>>>(p, B, qpc, nqg, (int)rows);
             return HS_OK;
         };
@@ -755,7 +766,8 @@ static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const do
         if (rc != HS_OK) return rc;
     } else {
         const size_t smem = (size_t)kTileDocs * (sizeof(double) + sizeof(uint32_t));
-        HS_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t smem_set[16] = {0};
+        HS_CUDA(hs_smem_limit(bm25_tile_kernel, smem, smem_set));
         bm25_tile_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
     }
     HS_LAUNCH_CHECK();
@@ -776,8 +788,9 @@ int hs_bm25plus_score(const hs_index* idx, const int32_t* q_terms, const double*
                            true, delta);
 }
 
-int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
-                       int32_t B, const int64_t* doc_ids, int32_t C, double* out, void* stream) {
+static int bm25_score_docs_impl(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                                int32_t B, const int64_t* doc_ids, int32_t C, double* out, void* stream, bool plus,
+                                double delta) {
     HS_REQUIRE(idx != nullptr, "hs_bm25_score_docs: idx is null");
     if (B == 0 || C == 0) return HS_OK;
     HS_REQUIRE(B > 0 && C > 0 && doc_ids != nullptr && out != nullptr, "hs_bm25_score_docs: bad arguments");
@@ -786,9 +799,26 @@ int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double
     if (rc != HS_OK) return rc;
     const int64_t warps = (int64_t)B * C;
     const int64_t blocks = (warps * 32 + 255) / 256;
-    bm25_docs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, doc_ids, C, out, B);
+    if (plus) {
+        HS_REQUIRE(idx->k1 >= 0.0 && idx->b >= 0.0 && idx->b <= 1.0 && idx->avgdl > 0.0,
+                   "hs_bm25plus_score_docs: needs k1 >= 0, 0 <= b <= 1 and a non-empty corpus");
+        p.delta = delta;
+        bm25_docs_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, doc_ids, C, out, B);
+    } else {
+        bm25_docs_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p, doc_ids, C, out, B);
+    }
     HS_LAUNCH_CHECK();
     return HS_OK;
+}
+
+int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                       int32_t B, const int64_t* doc_ids, int32_t C, double* out, void* stream) {
+    return bm25_score_docs_impl(idx, q_terms, q_idf, q_off, B, doc_ids, C, out, stream, false, 0.0);
+}
+
+int hs_bm25plus_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                           int32_t B, const int64_t* doc_ids, int32_t C, double delta, double* out, void* stream) {
+    return bm25_score_docs_impl(idx, q_terms, q_idf, q_off, B, doc_ids, C, out, stream, true, delta);
 }
 
 }  // extern "C"

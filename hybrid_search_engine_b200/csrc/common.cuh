@@ -25,6 +25,8 @@ struct hs_index {
     int64_t ld_bf16 = 0;
     CUtensorMap tmap_a;          // TMA descriptor over v_bf16: box 64 x 128, 128-byte swizzle
     bool has_tmap_a = false;
+    CUtensorMap tmap_f32;        // TMA descriptor over the float32 matrix: box 32 x 128 (tf32x3 GEMM path)
+    bool has_tmap_f32 = false;
     // csr
     const int64_t* indptr = nullptr;
     const uint2* postings = nullptr;
@@ -37,6 +39,8 @@ struct hs_index {
     uint32_t tf_cap = 0;
     double avgdl = 0.0, k1 = 1.5, b = 0.75;
 };
+
+void hs_gemm_attach_f32(hs_index* idx);      // dense_gemm.cu: builds tmap_f32 (called by hs_index_set_dense)
 
 // ---------------------------------------------------------------- error plumbing
 void hs_set_error(const char* fmt, ...);
@@ -117,6 +121,20 @@ __device__ __forceinline__ float hs_warp_sum_f32(float v) {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xFFFFFFFFu, v, m));
     return v;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a kernel needs more than it was last given on
+// this device: `cache` is a function-local static of the launching function (one per kernel instantiation),
+// so the steady-state hot path makes no attribute call at all
+template <typename Kern>
+static inline cudaError_t hs_smem_limit(Kern kern, size_t smem, size_t (&cache)[16]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& have = cache[dev & 15];
+    if (smem <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) have = smem;
+    return e;
 }
 
 static inline int hs_num_sms(int device) {

@@ -331,7 +331,8 @@ int launch_dense(const DenseParams& p, int num_sms, cudaStream_t st) {
     constexpr int G = 1 << LG;
     const size_t smem = (size_t)kStages * G * p.ld * sizeof(float) + 2 * kStages * sizeof(uint64_t);
     auto kern = dense_scan_kernel<NCHUNK, BQ, EXACT, LG, QG>;
-    HS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set[16] = {0};                 // per instantiation: the attribute is set once, not per launch
+    HS_CUDA(hs_smem_limit(kern, smem, smem_set));
     const int64_t n_tiles = (p.n + G - 1) / G;
     const int grid = (int)((n_tiles < num_sms) ? n_tiles : num_sms);
     kern<<<grid, kThreads, smem, st>>>(p);
@@ -442,7 +443,8 @@ int hs_dense_scan(const hs_index* idx, const float* queries, int32_t B, int64_t 
         while (bq > B - b0) bq >>= 1;
         int qg = 4;
         while (qg > 1 && bq * qg > B - b0) qg >>= 1;
-        if (const char* f = getenv("HS_DENSE_FORCE")) {      // tuning aid: "bq,qg"
+        static const char* const force = getenv("HS_DENSE_FORCE");      // tuning aid "bq,qg", read once
+        if (const char* f = force) {
             int fb = 0, fq = 0;
             if (sscanf(f, "%d,%d", &fb, &fq) == 2 && fb >= 1 && fb <= cap && fb * fq <= B - b0 &&
                 (fq == 1 || fq == 2 || fq == 4) && (fb & (fb - 1)) == 0) {

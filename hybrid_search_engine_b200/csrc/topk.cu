@@ -170,6 +170,7 @@ struct FuseParams {
     unsigned long long* gthr;   // [B] published lower bounds on the k-th best key (zeroed per call)
     uint64_t* blockmax;         // [B, kBoundBlocks] best key of each sampled block (workspace)
     int64_t n, doc_base;
+    int64_t ld;                 // row stride of a and b (elements)
     int mode, k, n_chunks;
     float wa32, wb32;
     double wa64;
@@ -268,8 +269,8 @@ __global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParam
     const int64_t start = (int64_t)blk * stride;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
-    const float* pa = p.a + (int64_t)b * p.n;
-    const float* pb = p.b ? p.b + (int64_t)b * p.n : nullptr;
+    const float* pa = p.a + (int64_t)b * p.ld;
+    const float* pb = p.b ? p.b + (int64_t)b * p.ld : nullptr;
     uint64_t best = 0;
 #pragma unroll
     for (int u = 0; u < kBoundDocs / 32; ++u) {
@@ -311,8 +312,8 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
     const int64_t hi = (lo + span < p.n) ? lo + span : p.n;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
-    const float* pa = p.a + (int64_t)b * p.n;
-    const float* pb = p.b ? p.b + (int64_t)b * p.n : nullptr;
+    const float* pa = p.a + (int64_t)b * p.ld;
+    const float* pb = p.b ? p.b + (int64_t)b * p.ld : nullptr;
     unsigned long long* gthr = p.gthr + b;
     if (tid == 0) overflow = 0;
     sel.init();
@@ -502,6 +503,64 @@ __global__ void __launch_bounds__(kThreads) topk_merge_walk_kernel(const uint64_
     for (int i = tid; i < k; i += kThreads) out[(int64_t)b * k + i] = sel.buf[i];
 }
 
+// thr[b] = score of the kth best key of query b (-inf when the list is shorter: no bound)
+__global__ void keys_kth_score_kernel(const uint64_t* __restrict__ keys, int B, int k, int kth, float* __restrict__ thr) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint64_t key = keys[(int64_t)b * k + kth - 1];
+    thr[b] = key != 0 ? hs_dec_f32((uint32_t)(key >> 32)) : __int_as_float(0xff800000);
+}
+
+// Candidate lists of the FILTER epilogue of the tensor-core scan (dense_gemm.cu) -> final ranking.  One CTA per
+// query: the best k_sel RAW keys (score = cosine) among the min(cnt, cap) appended candidates and n_extra keys from
+// elsewhere (the sample pass that produced the threshold), then -- HS_FUSE_SEARCHER -- every survivor is re-keyed with
+// the fused score f32(minmax(cos) * f32(w_a)) (core.py:264-268 with lexical weight 0) under the FINAL stats and the
+// list is sorted again; the best k_out go out.  k_sel > k_out covers fused-score ties at the cut (the map cos -> fused
+// score is monotone but not injective).  cnt > cap raises *overflow: the caller must redo the batch unfiltered.
+template <int KP>
+__global__ void __launch_bounds__(kThreads) cand_select_kernel(const uint64_t* __restrict__ cand,
+                                                               const uint32_t* __restrict__ cand_cnt, int cap,
+                                                               const uint64_t* __restrict__ extra, int n_extra,
+                                                               const FuseParams p, int k_sel, int k_out,
+                                                               uint64_t* __restrict__ out, int32_t* overflow) {
+    __shared__ Selector<KP> sel;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    sel.init();
+    uint32_t cnt = cand_cnt[b];
+    if (cnt > (uint32_t)cap) {
+        if (tid == 0) atomicOr(overflow, 1);
+        cnt = (uint32_t)cap;
+    }
+    const int64_t total = (int64_t)cnt + n_extra;
+    for (int64_t base = 0; base < total; base += kThreads * kItems) {
+        uint64_t key[kItems];
+#pragma unroll
+        for (int j = 0; j < kItems; ++j) {
+            const int64_t i = base + j * kThreads + tid;
+            key[j] = 0;
+            if (i < (int64_t)cnt) key[j] = cand[(int64_t)b * cap + i];
+            else if (i < total) key[j] = extra[(int64_t)b * n_extra + (i - cnt)];
+        }
+        sel.push(key, k_sel);
+    }
+    sel.finish(k_sel);
+    if (p.mode != HS_FUSE_RAW) {
+        const FuseConsts c = load_consts(p, b);
+        for (int i = tid; i < KP; i += kThreads) {
+            const uint64_t key = sel.buf[i];
+            uint64_t nk = 0;
+            if (i < k_sel && key != 0) {
+                const float cosv = hs_dec_f32((uint32_t)(key >> 32));
+                nk = hs_make_key(fuse_score(p, c, cosv, 0.f), 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu));
+            }
+            sel.buf[i] = nk;
+        }
+        __syncthreads();
+        bitonic_sort_desc_n(sel.buf, KP);
+    }
+    for (int i = tid; i < k_out; i += kThreads) out[(int64_t)b * k_out + i] = sel.buf[i];
+}
+
 int n_chunks_for(int64_t n) {
     int64_t c = (n + kChunkDocs - 1) / kChunkDocs;
     if (c < 1) c = 1;
@@ -536,27 +595,25 @@ size_t hs_fuse_topk_workspace_bytes(int64_t n_docs, int32_t B, int32_t k) {
     return ((size_t)B * n_chunks_for(n_docs) * (size_t)k + (size_t)B + (size_t)B * kBoundBlocks) * sizeof(uint64_t);
 }
 
-int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const float* b,
-                 const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
-                 const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
-                 void* stream) {
-    HS_REQUIRE(idx != nullptr, "hs_fuse_topk: idx is null");
+static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t fuse_mode, const float* a, const float* b,
+                          const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
+                          const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                          cudaStream_t st) {
     HS_REQUIRE(B > 0 && B <= 65535 && k > 0 && k <= HS_TOPK_MAX, "hs_fuse_topk: B=%d k=%d out of range (k <= %d)", B,
                k, HS_TOPK_MAX);
     HS_REQUIRE(out_keys != nullptr, "hs_fuse_topk: out_keys is null");
-    cudaStream_t st = (cudaStream_t)stream;
-    if (idx->n_docs == 0) {
+    if (n_docs == 0) {
         HS_CUDA(cudaMemsetAsync(out_keys, 0, (size_t)B * k * sizeof(uint64_t), st));
         return HS_OK;
     }
-    HS_REQUIRE(a != nullptr, "hs_fuse_topk: a is null");
+    HS_REQUIRE(a != nullptr && ld >= n_docs, "hs_fuse_topk: a is null or row stride < n_docs");
     HS_REQUIRE(fuse_mode == HS_FUSE_RAW || fuse_mode == HS_FUSE_SEARCHER || fuse_mode == HS_FUSE_HYBRID_BM25,
                "hs_fuse_topk: unknown fuse_mode %d", fuse_mode);
     HS_REQUIRE(fuse_mode == HS_FUSE_RAW || stats_enc != nullptr, "hs_fuse_topk: stats_enc is null");
     HS_REQUIRE(fuse_mode != HS_FUSE_HYBRID_BM25 || b != nullptr, "hs_fuse_topk: hybrid_bm25 needs b");
     HS_REQUIRE(fuse_mode != HS_FUSE_SEARCHER || b != nullptr || w_b == 0.0,
                "hs_fuse_topk: searcher fusion with w_b != 0 needs b");
-    const size_t need = hs_fuse_topk_workspace_bytes(idx->n_docs, B, k);
+    const size_t need = hs_fuse_topk_workspace_bytes(n_docs, B, k);
     HS_REQUIRE(workspace != nullptr && workspace_bytes >= need, "hs_fuse_topk: workspace too small (%zu < %zu)",
                workspace_bytes, need);
     FuseParams p;
@@ -568,17 +625,19 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
     p.blockmax = (uint64_t*)workspace + B;
     p.cand = (uint64_t*)workspace + B + (size_t)B * kBoundBlocks;
     HS_CUDA(cudaMemsetAsync(p.gthr, 0, (size_t)B * sizeof(uint64_t), st));
-    p.n = idx->n_docs;
-    p.doc_base = idx->doc_base;
+    p.n = n_docs;
+    p.ld = ld;
+    p.doc_base = doc_base;
     p.mode = fuse_mode;
     p.k = k;
-    p.n_chunks = n_chunks_for(idx->n_docs);
+    p.n_chunks = n_chunks_for(n_docs);
     p.wa32 = (float)w_a;   // numpy: float32 array * python float -> float32(w)
     p.wb32 = (float)w_b;
     p.wa64 = w_a;
     dim3 grid((unsigned)p.n_chunks, (unsigned)B);
     // starting bound from block maxima when the shard is large enough for it to pay (see above)
-    if (idx->n_docs >= (int64_t)kBoundBlocks * kBoundDocs * 4 && k <= kBoundBlocks / 2 && getenv("HS_NO_BOUND") == nullptr) {
+    static const bool no_bound = getenv("HS_NO_BOUND") != nullptr;      // A/B switch, read once
+    if (n_docs >= (int64_t)kBoundBlocks * kBoundDocs * 4 && k <= kBoundBlocks / 2 && !no_bound) {
         dim3 bg(kBoundBlocks / (kThreads / 32), (unsigned)B);
         fuse_blockmax_kernel<<<bg, kThreads, 0, st>>>(p);
         fuse_bound_kernel<<<B, kThreads, 0, st>>>(p);
@@ -593,6 +652,56 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
     HS_LAUNCH_CHECK();
     // candidate layout [B, n_chunks, k]: list stride k, query stride n_chunks * k
     return merge_dispatch(p.cand, p.n_chunks, B, k, (int64_t)k, (int64_t)p.n_chunks * k, out_keys, st);
+}
+
+int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const float* b,
+                 const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
+                 const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
+                 void* stream) {
+    HS_REQUIRE(idx != nullptr, "hs_fuse_topk: idx is null");
+    return fuse_topk_impl(idx->n_docs, idx->doc_base, idx->n_docs, fuse_mode, a, b, stats_enc, w_a, w_b, B, k, below_key,
+                          workspace, workspace_bytes, out_keys, (cudaStream_t)stream);
+}
+
+int hs_topk_select(const float* x, int64_t n, int64_t ld, int64_t doc_base, int32_t B, int32_t k, void* workspace,
+                   size_t workspace_bytes, uint64_t* out_keys, void* stream) {
+    HS_REQUIRE(n >= 0 && doc_base >= 0 && n + doc_base <= 0xFFFFFFFFll, "hs_topk_select: doc ids must fit uint32");
+    return fuse_topk_impl(n, doc_base, ld, HS_FUSE_RAW, x, nullptr, nullptr, 1.0, 0.0, B, k, nullptr, workspace,
+                          workspace_bytes, out_keys, (cudaStream_t)stream);
+}
+
+int hs_keys_kth_score(const uint64_t* keys, int32_t B, int32_t k, int32_t kth, float* thr, void* stream) {
+    HS_REQUIRE(keys != nullptr && thr != nullptr && B > 0 && kth >= 1 && kth <= k, "hs_keys_kth_score: bad arguments");
+    keys_kth_score_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(keys, B, k, kth, thr);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+
+int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t cand_cap, const uint64_t* extra_keys,
+                   int32_t n_extra, int32_t fuse_mode, const uint32_t* stats_enc, double w_a, int32_t B, int32_t k_sel,
+                   int32_t k_out, uint64_t* out_keys, int32_t* overflow, void* stream) {
+    HS_REQUIRE(cand != nullptr && cand_cnt != nullptr && cand_cap > 0 && out_keys != nullptr && overflow != nullptr,
+               "hs_cand_select: null pointer");
+    HS_REQUIRE(B > 0 && k_out > 0 && k_out <= k_sel && k_sel <= HS_TOPK_MAX && n_extra >= 0 &&
+                   (n_extra == 0 || extra_keys != nullptr),
+               "hs_cand_select: bad sizes (k_out=%d k_sel=%d)", k_out, k_sel);
+    HS_REQUIRE(fuse_mode == HS_FUSE_RAW || (fuse_mode == HS_FUSE_SEARCHER && stats_enc != nullptr),
+               "hs_cand_select: fuse_mode must be RAW or SEARCHER (with stats)");
+    FuseParams p;
+    memset(&p, 0, sizeof(p));
+    p.stats = stats_enc;
+    p.mode = fuse_mode;
+    p.wa32 = (float)w_a;
+    p.wa64 = w_a;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k_sel <= 128)
+        cand_select_kernel<128><<<B, kThreads, 0, st>>>(cand, cand_cnt, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
+    else if (k_sel <= 512)
+        cand_select_kernel<512><<<B, kThreads, 0, st>>>(cand, cand_cnt, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
+    else
+        cand_select_kernel<2048><<<B, kThreads, 0, st>>>(cand, cand_cnt, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
 }
 
 int hs_topk_merge(const uint64_t* keys, int32_t n_lists, int32_t B, int32_t k, uint64_t* out_keys, void* stream) {

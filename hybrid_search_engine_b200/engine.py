@@ -54,6 +54,7 @@ class SearchEngine:
         self.dense_mode = dense_mode
         self._bufs = {}
         self._pin_slot = 0         # which set of pinned staging buffers the uploads use (search_*_stream)
+        self._pin_events = {}      # (slot, group) -> event recorded after the last H2D copy out of that staging set
         self.launches = 0          # kernels launched by this engine (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------ buffers (never on the hot path twice)
@@ -78,43 +79,78 @@ class SearchEngine:
         return t[:need].view(*shape)
 
     # ------------------------------------------------------------------ query upload
+    # The H2D copies are asynchronous and queue behind whatever the stream is still running, so the host must not
+    # rewrite a pinned staging set before the copies out of it have executed: every upload waits for the event of
+    # the previous upload from the same set first (a no-op unless the GPU is more than one upload behind).
+    def _pin_wait(self, group: str):
+        ev = self._pin_events.get((self._pin_slot, group))
+        if ev is not None:
+            ev.synchronize()
+
+    def _pin_mark(self, group: str):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._pin_events[(self._pin_slot, group)] = ev
+
     def upload_vectors(self, q: np.ndarray) -> torch.Tensor:
         q = np.ascontiguousarray(q, dtype=np.float32)
         if q.ndim != 2 or q.shape[1] != self.shard.dim:
             raise ValueError(f"query vectors must be [B, {self.shard.dim}], got {q.shape}")
+        self._pin_wait("qv")
         pin = self._pinned("qv", q.shape, torch.float32)
         pin.copy_(torch.from_numpy(q))
         dev = self._buf("qv", q.shape, torch.float32)
         dev.copy_(pin, non_blocking=True)
+        self._pin_mark("qv")
         return dev
 
     def upload_terms(self, term_ids: Sequence[Sequence[int]]):
         """-> (q_terms int32 [T], q_idf float64 [T], q_off int32 [B+1]) on the device."""
+        (d_t, d_i, d_o, T), = self.upload_terms_split(term_ids, max(len(term_ids), 1))
+        self._n_tokens = T          # host copy of q_off[B] for the kernel's workspace sizing
+        return d_t, d_i, d_o
+
+    def upload_terms_split(self, term_ids: Sequence[Sequence[int]], per: int):
+        """One upload for the whole batch, sliced on the device into sub-batches of ``per`` queries:
+        -> [(q_terms int32 [T_s], q_idf float64 [T_s], q_off int32 [nb_s + 1] (rebased to 0), T_s), ...]."""
         idf = self.shard.idf_host
         df = self.shard.df_host
-        off = [0]
+        nq = len(term_ids)
         flat: List[int] = []
-        for ids in term_ids:
-            # bm25.py:100 -- terms that are in no document have no idf entry and are skipped
-            flat.extend(int(t) for t in ids if 0 <= int(t) < len(df) and df[int(t)] > 0)
-            off.append(len(flat))
+        offs: List[int] = []            # concatenated, each sub-batch starting again at 0
+        cuts = []                       # (token start, offset start, nb) per sub-batch
+        for s in range(0, max(nq, 1), per):
+            t0 = len(flat)
+            cuts.append((t0, len(offs), min(nq, s + per) - s))
+            offs.append(0)
+            for ids in term_ids[s:s + per]:
+                # bm25.py:100 -- terms that are in no document have no idf entry and are skipped
+                flat.extend(int(t) for t in ids if 0 <= int(t) < len(df) and df[int(t)] > 0)
+                offs.append(len(flat) - t0)
         T = len(flat)
+        self._pin_wait("qt")
         pin_t = self._pinned("qt", (max(T, 1),), torch.int32)
         pin_i = self._pinned("qi", (max(T, 1),), torch.float64)
-        pin_o = self._pinned("qo", (len(off),), torch.int32)
+        pin_o = self._pinned("qo", (len(offs),), torch.int32)
         if T:
             arr = np.asarray(flat, dtype=np.int64)
             pin_t[:T].copy_(torch.from_numpy(arr.astype(np.int32)))
             pin_i[:T].copy_(torch.from_numpy(idf[arr]))
-        pin_o.copy_(torch.tensor(off, dtype=torch.int32))
+        pin_o.copy_(torch.tensor(offs, dtype=torch.int32))
         d_t = self._buf("qt", (max(T, 1),), torch.int32)
         d_i = self._buf("qi", (max(T, 1),), torch.float64)
-        d_o = self._buf("qo", (len(off),), torch.int32)
+        d_o = self._buf("qo", (len(offs),), torch.int32)
         d_t.copy_(pin_t, non_blocking=True)
         d_i.copy_(pin_i, non_blocking=True)
         d_o.copy_(pin_o, non_blocking=True)
-        self._n_tokens = T          # host copy of q_off[B] for the kernel's workspace sizing
-        return d_t, d_i, d_o
+        self._pin_mark("qt")
+        out = []
+        for i, (t0, o0, nb) in enumerate(cuts):
+            t1 = cuts[i + 1][0] if i + 1 < len(cuts) else T
+            # empty slices keep a valid (never dereferenced) pointer
+            out.append((d_t[t0:max(t1, t0 + 1)] if T else d_t, d_i[t0:max(t1, t0 + 1)] if T else d_i,
+                        d_o[o0:o0 + nb + 1], t1 - t0))
+        return out
 
     # ------------------------------------------------------------------ kernels
     def _stats(self, B: int) -> torch.Tensor:
@@ -127,22 +163,36 @@ class SearchEngine:
         B = q_dev.shape[0]
         cos = self._buf("cos", (B, self.shard.n_docs), torch.float32)
         m = DENSE_MODES[mode or self.dense_mode]
-        if m == _lib.HS_DENSE_BF16:
-            self.shard.ensure_bf16()
-            nbytes = self.lib.hs_dense_scan_bf16_workspace_bytes(self.shard.handle, B)
-            ws = self._buf("gemm_ws", (max(nbytes // 8, 1) + 32,), torch.int64)
-            off = (-ws.data_ptr()) % 256                           # 256-byte aligned view
-            check(self.lib.hs_dense_scan_bf16(self.shard.handle, ptr(q_dev), B, q_dev.stride(0),
-                                              ws.data_ptr() + off, nbytes, ptr(cos), ptr(stats),
-                                              stream_ptr(self.device)), "hs_dense_scan_bf16")
-            self.launches += 2 * ((B + 127) // 128)
+        if m in (_lib.HS_DENSE_BF16, _lib.HS_DENSE_TF32X3):          # tensor-core GEMM (K2b)
+            wsp, nbytes = self._gemm_ws(B, m)
+            n = self.shard.n_docs
+            check(self.lib.hs_dense_gemm(self.shard.handle, ptr(q_dev), B, q_dev.stride(0), m, 0, n, wsp, nbytes,
+                                         ptr(cos), n, ptr(stats), stream_ptr(self.device)), "hs_dense_gemm")
+            self.launches += 2 * self._gemm_passes(B, m)
             return cos
         check(self.lib.hs_dense_scan(self.shard.handle, ptr(q_dev), B, q_dev.stride(0), m, ptr(cos), ptr(stats),
                                      stream_ptr(self.device)), "hs_dense_scan")
         self.launches += self.dense_launches(B, mode)
         return cos
 
+    def _gemm_ws(self, B: int, m: int):
+        """(256-byte aligned workspace pointer, bytes) for the tensor-core scan; builds the bf16 copy on first use."""
+        if m == _lib.HS_DENSE_BF16:
+            self.shard.ensure_bf16()
+        nbytes = self.lib.hs_dense_gemm_workspace_bytes(self.shard.handle, B, m)
+        ws = self._buf("gemm_ws", (max(nbytes // 8, 1) + 32,), torch.int64)
+        return ws.data_ptr() + (-ws.data_ptr()) % 256, nbytes
+
+    @staticmethod
+    def _gemm_passes(B: int, m: int) -> int:
+        """Corpus passes of one GEMM call: 256 queries per pass in bf16 (two query tiles), 128 in tf32x3."""
+        per = 256 if m == _lib.HS_DENSE_BF16 else 128
+        return (B + per - 1) // per
+
     def dense_launches(self, B: int, mode: Optional[str] = None) -> int:
+        m = DENSE_MODES[mode or self.dense_mode]
+        if m in (_lib.HS_DENSE_BF16, _lib.HS_DENSE_TF32X3):
+            return self._gemm_passes(B, m)
         nchunk = (self.shard.dim + 127) // 128
         nchunk = nchunk if nchunk <= 4 else (6 if nchunk <= 6 else 8)
         budget, cap = 12, 4
@@ -204,15 +254,20 @@ class SearchEngine:
                                     B, k, ptr(below), ptr(ws), ws_bytes, ptr(keys), stream_ptr(self.device)),
               "hs_fuse_topk")
         self.launches += 2 if n > 0 else 0
-        if self.group is not None and self.world > 1:
-            from .parallel import allgather_keys
-            gathered = allgather_keys(keys, self.group, self._buf("keys_all", (self.world, B, k), torch.int64))  # C1
-            merged = self._buf("keys_merged", (B, k), torch.int64)
-            check(self.lib.hs_topk_merge(ptr(gathered), self.world, B, k, ptr(merged),
-                                         stream_ptr(self.device)), "hs_topk_merge")
-            self.launches += 1
-            keys = merged
-        return keys
+        return self._merge_across(keys)
+
+    def _merge_across(self, keys: torch.Tensor) -> torch.Tensor:
+        """C1: all-gather of the per-shard key lists [B, k] + merge kernel; identity on a single shard."""
+        if self.group is None or self.world == 1:
+            return keys
+        from .parallel import allgather_keys
+        B, k = keys.shape
+        gathered = allgather_keys(keys, self.group, self._buf("keys_all", (self.world, B, k), torch.int64))
+        merged = self._buf("keys_merged", (B, k), torch.int64)
+        check(self.lib.hs_topk_merge(ptr(gathered), self.world, B, k, ptr(merged),
+                                     stream_ptr(self.device)), "hs_topk_merge")
+        self.launches += 1
+        return merged
 
     def unpack(self, keys: torch.Tensor):
         B, k = keys.shape
@@ -283,9 +338,86 @@ class SearchEngine:
         finally:
             self._pin_slot = 0
 
-    def search_semantic(self, qb: QueryBatch, k: int, sw: float = 1.0, dense_mode: Optional[str] = None):
-        """Searcher.search with lexical weight 0 (pipelines.py:317-324,474-481): min-max cosine * sw."""
+    def search_semantic(self, qb: QueryBatch, k: int, sw: float = 1.0, dense_mode: Optional[str] = None,
+                        filtered: Optional[bool] = None):
+        """Searcher.search with lexical weight 0 (pipelines.py:317-324,474-481): min-max cosine * sw.
+
+        In the tensor-core modes on a large shard the select's pre-filter runs inside the GEMM epilogue
+        (``_semantic_filtered``): no [B, n] score matrix is written or re-read.  ``filtered`` forces the choice."""
+        mode = dense_mode or self.dense_mode
+        if filtered is None:
+            filtered = (mode in ("bf16", "tf32x3") and self.shard.n_docs >= self.FILTER_MIN_DOCS
+                        and 0 < k <= HS_TOPK_MAX - 64)
+        if filtered:
+            out = self._semantic_filtered(qb, k, sw, mode)
+            if out is not None:
+                return out
         return self._run(qb, k, HS_FUSE_SEARCHER, sw, 0.0, True, False, dense_mode)
+
+    FILTER_MIN_DOCS = 1 << 18       # below this the stored-matrix path is just as fast
+    FILTER_GROUP = 512              # queries per candidate-buffer set (two bf16 corpus passes)
+
+    def _semantic_filtered(self, qb: QueryBatch, k: int, sw: float, mode: str):
+        """Pure-semantic top-k with the candidate filter fused into the GEMM epilogue (hs_dense_gemm_filter).
+
+        Per group of queries, all on the stream:  (1) GEMM over a sample block of the shard (docs [0, S), stored);
+        (2) exact top-k_sel of the sample -> its k_sel-th score is a valid lower bound ``thr`` on the k_sel-th best
+        score of the whole shard (k_sel real docs reach it);  (3) GEMM over docs [S, n) whose epilogue appends the
+        (query, doc) pairs with cos >= thr as ranking keys (~k_sel * n / S per query) and folds min/max;
+        (4) [sharded] C2;  (5) hs_cand_select: best k_sel by cosine among candidates + sample keys, re-keyed with
+        the fused score under the final stats, best k out;  (6) [sharded] C1.  Bit-identical to the stored-matrix
+        path (tests/test_gpu_gemm.py); returns None when a candidate list overflowed (caller redoes it unfiltered)."""
+        B, n = len(qb), self.shard.n_docs
+        m = DENSE_MODES[mode]
+        k_sel = 128 if k <= 100 else (512 if k <= 480 else 2048)
+        S = min(max(32768, n // 64), n // 2)
+        S = (S + 127) // 128 * 128
+        cap = 1 << max(12, (4 * k_sel * ((n - S + S - 1) // S)).bit_length())      # ~4-8x the expected count
+        st = stream_ptr(self.device)
+        out_s, out_i = [], []
+        with torch.cuda.device(self.device):
+            qd_all = self.upload_vectors(qb.vectors)
+            overflow = self._buf("cand_ovf", (1,), torch.int32)
+            overflow.zero_()
+            group = self.FILTER_GROUP if k_sel == 128 else (128 if k_sel == 512 else 32)   # bounds the candidate buffers
+            for s in range(0, B, group):
+                e = min(B, s + group)
+                nb = e - s
+                qd = qd_all[s:e]
+                stats = self._stats(nb)
+                wsp, nbytes = self._gemm_ws(nb, m)
+                cos_s = self._buf("cos_sample", (nb, S), torch.float32)
+                check(self.lib.hs_dense_gemm(self.shard.handle, ptr(qd), nb, qd.stride(0), m, 0, S, wsp, nbytes,
+                                             ptr(cos_s), S, ptr(stats), st), "hs_dense_gemm")
+                ws_bytes = self.lib.hs_fuse_topk_workspace_bytes(S, nb, k_sel)
+                ws = self._buf("topk_ws", (max(ws_bytes // 8, 1),), torch.int64)
+                keys_s = self._buf("keys_sample", (nb, k_sel), torch.int64)
+                check(self.lib.hs_topk_select(ptr(cos_s), S, S, self.shard.doc_base, nb, k_sel, ptr(ws), ws_bytes,
+                                              ptr(keys_s), st), "hs_topk_select")
+                thr = self._buf("cand_thr", (nb,), torch.float32)
+                check(self.lib.hs_keys_kth_score(ptr(keys_s), nb, k_sel, k_sel, ptr(thr), st), "hs_keys_kth_score")
+                cand = self._buf("cand", (nb, cap), torch.int64)
+                cnt = self._buf("cand_cnt", (nb,), torch.int32)
+                cnt.zero_()
+                check(self.lib.hs_dense_gemm_filter(self.shard.handle, ptr(qd), nb, qd.stride(0), m, S, n, wsp, nbytes,
+                                                    ptr(thr), ptr(cand), cap, ptr(cnt), ptr(stats), st),
+                      "hs_dense_gemm_filter")
+                stats = self._exchange_stats(stats, nb)
+                keys = self._buf("keys", (nb, k), torch.int64)
+                check(self.lib.hs_cand_select(ptr(cand), ptr(cnt), cap, ptr(keys_s), k_sel, HS_FUSE_SEARCHER, ptr(stats),
+                                              float(sw), nb, k_sel, k, ptr(keys), ptr(overflow), st), "hs_cand_select")
+                self.launches += 4 * self._gemm_passes(nb, m) + 7
+                sc, ids = self.unpack(self._merge_across(keys))
+                out_s.append(sc.clone() if B > group else sc)
+                out_i.append(ids.clone() if B > group else ids)
+            if self.group is not None and self.world > 1:      # every rank must take the same branch below
+                import torch.distributed as dist
+                dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=self.group)
+            if int(overflow.item()) != 0:          # a candidate list overflowed: results may miss docs
+                return None
+        if len(out_s) == 1:
+            return out_s[0], out_i[0]
+        return torch.cat(out_s), torch.cat(out_i)
 
     def search_searcher(self, qb: QueryBatch, lex: np.ndarray, k: int, sw: float, lw: float,
                         dense_mode: Optional[str] = None):
@@ -321,24 +453,27 @@ class SearchEngine:
             out = self._select(HS_FUSE_SEARCHER, sparse, bm, stats, sw, lw if bm is not None else 0.0, k)
             return self.unpack(out)
 
-    def search_bm25(self, qb: QueryBatch, k: int):
-        """BM25.search (bm25.py:129-142): raw float32 BM25 score, canonical tie order."""
-        return self._run(qb, k, HS_FUSE_RAW, 1.0, 0.0, False, True, None)
+    def search_bm25(self, qb: QueryBatch, k: int, plus_delta: Optional[float] = None):
+        """BM25.search (bm25.py:129-142): raw float32 BM25 score, canonical tie order (BM25Plus with ``plus_delta``)."""
+        return self._run(qb, k, HS_FUSE_RAW, 1.0, 0.0, False, True, None, plus_delta=plus_delta)
 
-    def _run(self, qb, k, mode, wa, wb, use_dense, use_bm25, dense_mode, lex=None):
+    def _run(self, qb, k, mode, wa, wb, use_dense, use_bm25, dense_mode, lex=None, plus_delta=None):
         B = len(qb)
         out_s, out_i = [], []
         with torch.cuda.device(self.device):
-            for s, e in self._batches(B):
+            # ONE upload of the whole batch before the sub-batch loop; the loop only slices device tensors (the
+            # staging buffers are never rewritten while a sub-batch that reads them is still queued)
+            qd_all = self.upload_vectors(qb.vectors) if use_dense else None
+            terms_all = self.upload_terms_split(qb.term_ids, self.max_batch) if use_bm25 else None
+            for bi, (s, e) in enumerate(self._batches(B)):
                 nb = e - s
                 stats = self._stats(nb)
                 cos = bm = None
                 if use_dense:
-                    qd = self.upload_vectors(qb.vectors[s:e])
-                    cos = self.dense_scan(qd, stats, dense_mode)
+                    cos = self.dense_scan(qd_all[s:e], stats, dense_mode)
                 if use_bm25:
-                    qt, qi, qo = self.upload_terms(qb.term_ids[s:e])
-                    bm = self.bm25_score(qt, qi, qo, nb, stats)
+                    qt, qi, qo, n_tok = terms_all[bi]
+                    bm = self.bm25_score(qt, qi, qo, nb, stats, n_tok, plus_delta=plus_delta)
                 if lex is not None:
                     if isinstance(lex, torch.Tensor):
                         bm = lex[s:e].to(self.device, torch.float32).contiguous()
@@ -383,15 +518,22 @@ class SearchEngine:
         return arr, (idf[arr] if len(arr) else np.zeros(0, np.float64)), np.asarray(off, dtype=np.int32)
 
     # ------------------------------------------------------------------ small kernels
-    def bm25_score_docs(self, term_ids: Sequence[Sequence[int]], doc_ids: torch.Tensor) -> torch.Tensor:
-        """BM25.score on candidate docs (pipelines.py:485).  doc_ids int64 [B, C] shard-local."""
+    def bm25_score_docs(self, term_ids: Sequence[Sequence[int]], doc_ids: torch.Tensor,
+                        plus_delta: Optional[float] = None) -> torch.Tensor:
+        """BM25.score on candidate docs (pipelines.py:485; BM25Plus.score with ``plus_delta``).
+        doc_ids int64 [B, C] shard-local."""
         B, Cn = doc_ids.shape
         with torch.cuda.device(self.device):
             qt, qi, qo = self.upload_terms(term_ids)
             out = self._buf("bm25_docs", (B, Cn), torch.float64)
-            check(self.lib.hs_bm25_score_docs(self.shard.handle, ptr(qt), ptr(qi), ptr(qo), B,
-                                              ptr(doc_ids.contiguous()), Cn, ptr(out), stream_ptr(self.device)),
-                  "hs_bm25_score_docs")
+            if plus_delta is not None:
+                check(self.lib.hs_bm25plus_score_docs(self.shard.handle, ptr(qt), ptr(qi), ptr(qo), B,
+                                                      ptr(doc_ids.contiguous()), Cn, float(plus_delta), ptr(out),
+                                                      stream_ptr(self.device)), "hs_bm25plus_score_docs")
+            else:
+                check(self.lib.hs_bm25_score_docs(self.shard.handle, ptr(qt), ptr(qi), ptr(qo), B,
+                                                  ptr(doc_ids.contiguous()), Cn, ptr(out), stream_ptr(self.device)),
+                      "hs_bm25_score_docs")
             self.launches += 1
         return out
 

@@ -139,7 +139,7 @@ class DeviceIndex:
             check(self.lib.hs_index_set_csr(self.handle, ptr(self.indptr), ptr(self.postings), self.n_terms,
                                             self.postings.shape[0]), "hs_index_set_csr")
             check(self.lib.hs_index_set_doc_stats(self.handle, ptr(self.dl), float(avgdl), self.k1, self.b,
-                                                  ptr(self.impact_table), self.max_dl, self.tf_cap),
+                                                  ptr(self.impact_table), self.max_dl, self.tf_cap, st),
                   "hs_index_set_doc_stats")
 
     # ------------------------------------------------------------------ persistence (checkpoint / resume)
@@ -150,21 +150,37 @@ class DeviceIndex:
         if self.vectors is not None:
             state["vectors"] = self.vectors[:, :self.dim].cpu()
         if self.indptr is not None:
-            state.update(indptr=self.indptr.cpu(), postings=self.postings.cpu(), dl=self.dl.cpu(), avgdl=self.avgdl,
-                         k1=self.k1, b=self.b, df=self.df_host, n_docs_global=self.n_docs_global, max_dl=self.max_dl)
+            # tensors and plain scalars only: the file loads with weights_only=True (no unpickling of objects)
+            state.update(indptr=self.indptr.cpu(), postings=self.postings.cpu(), dl=self.dl.cpu(),
+                         avgdl=float(self.avgdl), k1=float(self.k1), b=float(self.b),
+                         df=torch.from_numpy(np.ascontiguousarray(self.df_host, dtype=np.int64)),
+                         n_docs_global=int(self.n_docs_global), max_dl=int(self.max_dl))
         torch.save(state, path)
 
     @classmethod
     def load(cls, path: str, device) -> "DeviceIndex":
-        state = torch.load(path, map_location="cpu", weights_only=False)
-        if state.get("format") != "hs_b200_shard_v1":
+        state = torch.load(path, map_location="cpu", weights_only=True)
+        if not isinstance(state, dict) or state.get("format") != "hs_b200_shard_v1":
             raise ValueError(f"{path}: not an hs_b200 shard file")
-        shard = cls(device, state["n_docs"], state["doc_base"])
+        n_docs, doc_base = int(state["n_docs"]), int(state["doc_base"])
+        if "vectors" in state:
+            v = state["vectors"]
+            if v.dim() != 2 or v.shape[0] != n_docs or v.shape[1] != int(state["dim"]):
+                raise ValueError(f"{path}: dense matrix {tuple(v.shape)} does not match n_docs={n_docs}, dim={state['dim']}")
+        if "indptr" in state:
+            indptr, postings, dl, df = state["indptr"], state["postings"], state["dl"], state["df"]
+            if (indptr.dim() != 1 or indptr.numel() < 1 or int(indptr[0]) != 0 or postings.dim() != 2
+                    or postings.shape[1] != 2 or int(indptr[-1]) != postings.shape[0] or dl.numel() != n_docs
+                    or df.numel() != indptr.numel() - 1 or bool((indptr[1:] < indptr[:-1]).any())):
+                raise ValueError(f"{path}: inconsistent CSR / doc statistics in shard file")
+            if postings.shape[0] and int(postings[:, 0].view(torch.int32).max()) >= n_docs:
+                raise ValueError(f"{path}: a posting names a doc outside the shard")
+        shard = cls(device, n_docs, doc_base)
         if "vectors" in state:
             shard.set_dense(state["vectors"].to(shard.device))
         if "indptr" in state:
-            shard.set_bm25(state["indptr"], state["postings"], state["dl"], state["avgdl"], state["df"],
-                           state["n_docs_global"], state["k1"], state["b"], max_dl=state["max_dl"])
+            shard.set_bm25(indptr, postings, dl, float(state["avgdl"]), df.numpy(), int(state["n_docs_global"]),
+                           float(state["k1"]), float(state["b"]), max_dl=int(state["max_dl"]))
         return shard
 
     @property

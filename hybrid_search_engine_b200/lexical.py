@@ -29,9 +29,10 @@ class LexicalScorer:
         self.n = 0
 
     def prepare(self, docs: Sequence[str]):
-        key = (id(docs), len(docs))
-        if self._key == key:
+        # identity of the caller's document list, held strongly (an id() of a freed list can be recycled)
+        if self._key is not None and self._key[0] is docs and self._key[1] == len(docs):
             return
+        key = (docs, len(docs))
         lowered = [d.lower() for d in docs]
         # code points (utf-32) of every lower-cased document, concatenated
         lens = np.fromiter((len(d) for d in lowered), dtype=np.int64, count=len(lowered))

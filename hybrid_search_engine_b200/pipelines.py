@@ -239,12 +239,11 @@ class MultiStagePipeline(BasePipeline):
         bm = eng.bm25_score_docs(terms, ids1)                                    # stage 2: float64 BM25.score
         ids_h, bm_h = ids1.cpu().numpy(), bm.cpu().numpy()
         contents = self.docs_df.contents
-        out = []
-        for qi in range(len(queries)):
-            # stable sort, descending: ties keep stage-1 rank (pipelines.py:486)
-            order = np.lexsort((np.arange(k1), -bm_h[qi]))[:self.stage2_k]
-            out.append([(float(bm_h[qi][j]), contents[int(ids_h[qi][j])], int(ids_h[qi][j])) for j in order])
-        return out
+        # stable sort, descending: ties keep stage-1 rank (pipelines.py:486) -- one vectorised sort for the batch
+        rank = np.broadcast_to(np.arange(k1), bm_h.shape)
+        order = np.lexsort((rank, -bm_h), axis=-1)[:, :self.stage2_k]
+        return [[(float(bm_h[qi][j]), contents[int(ids_h[qi][j])], int(ids_h[qi][j])) for j in order[qi]]
+                for qi in range(len(queries))]
 
     def search(self, query: str, top_k: int = None, *, query_vector=None) -> PipelineResult:
         qv = None if query_vector is None else np.asarray(query_vector, np.float32)[None, :]

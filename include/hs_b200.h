@@ -42,7 +42,8 @@ typedef enum {
 typedef enum {
     HS_DENSE_EXACT = 0,    /* float64 accumulation in the conformance order: bit-identical to oracle */
     HS_DENSE_FP32 = 1,     /* float32 FMA accumulation, same lane order (as precise as the reference) */
-    HS_DENSE_BF16 = 2      /* bf16 tcgen05 GEMM at large query batch (stage-1 retrieval, 1e-2) */
+    HS_DENSE_BF16 = 2,     /* bf16 tcgen05 GEMM at large query batch (stage-1 retrieval, 1e-2) */
+    HS_DENSE_TF32X3 = 3    /* 3xTF32 tcgen05 GEMM on the float32 matrix: float32-grade accuracy at large batch */
 } hs_dense_mode;
 
 /* score fusion formulas */
@@ -71,10 +72,10 @@ int hs_index_set_csr(hs_index* idx, const int64_t* indptr, const uint32_t* posti
 /* doc lengths u32[n_docs] after stop-word removal (bm25.py:59-60), corpus-global avgdl (bm25.py:71),
  * k1, b (bm25.py:19-33); impact_table double[(max_dl+1) * (tf_cap+1)] from hs_bm25_impact_table, or
  * NULL to compute every posting inline.  With a table the call checks max(dl) <= max_dl on the device
- * (synchronous, index time) because the scoring kernels index the table by doc length unchecked; the
+ * (index time: ordered on `stream`, the stream dl and the table were produced on, then synchronised) because the scoring kernels index the table by doc length unchecked; the
  * kernels keep a copy of the table in shared memory when (max_dl+1) * ((tf_cap+1)|1) <= ~10 000 entries */
 int hs_index_set_doc_stats(hs_index* idx, const uint32_t* dl, double avgdl, double k1, double b,
-                           const double* impact_table, uint32_t max_dl, uint32_t tf_cap);
+                           const double* impact_table, uint32_t max_dl, uint32_t tf_cap, void* stream);
 
 /* ---- index-time kernels ------------------------------------------------------------------------ */
 /* vnorm[i] = f32(sqrt(sum64 v[i,:]^2)), conformance order (utils.py:47 np.linalg.norm per row) */
@@ -103,13 +104,24 @@ int hs_stats_fold_minmax(const float* x, int64_t n, int32_t B, int32_t slot_min,
 int hs_dense_scan(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
                   float* cos, uint32_t* stats_enc, void* stream);
 
-/* K2b the same scan at large query batch as a bf16 tcgen05 GEMM (HS_DENSE_BF16): needs a bf16 copy of
- *     the matrix, [n_docs, ld_bf16] with ld_bf16 a multiple of 64 (zero padded).  Norms stay float32.
- *     Agrees with the float32 path within 1e-2; used for stage-1 retrieval at batch >= 32. */
+/* K2b the same scan at large query batch on the tensor cores (tcgen05 GEMM, one corpus pass serves 128-256
+ *     queries) over the doc range [doc_lo, doc_hi) of the shard:
+ *       HS_DENSE_BF16    needs a bf16 copy of the matrix, [n_docs, ld_bf16] with ld_bf16 a multiple of 64 (zero
+ *                        padded); agrees with the float32 path within 1e-2 (stage-1 retrieval)
+ *       HS_DENSE_TF32X3  reads the float32 matrix itself, split hi/lo on the fly: float32-grade accuracy
+ *     Norms stay float32.  cos[b, i - doc_lo] float32 with row stride cos_ld; min/max folded into stats. */
 int hs_index_set_dense_bf16(hs_index* idx, const void* v_bf16, int64_t ld_bf16);
-size_t hs_dense_scan_bf16_workspace_bytes(const hs_index* idx, int32_t B);
-int hs_dense_scan_bf16(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, void* workspace,
-                       size_t workspace_bytes, float* cos, uint32_t* stats_enc, void* stream);
+size_t hs_dense_gemm_workspace_bytes(const hs_index* idx, int32_t B, int32_t mode);
+int hs_dense_gemm(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t doc_lo,
+                  int64_t doc_hi, void* workspace, size_t workspace_bytes, float* cos, int64_t cos_ld,
+                  uint32_t* stats_enc, void* stream);
+/* the same GEMM with the select's pre-filter fused into its epilogue (pure-semantic retrieval: Searcher.search with
+ * lexical weight 0, multi_stage stage 1, pipelines.py:474-481): nothing is stored; every (query, doc) cosine >=
+ * thr[b] (NULL: all) is appended as a ranking key to cand[b, 0..cand_cap) with cand_cnt[b] counting the appends
+ * (zero it first; > cand_cap afterwards = overflow, the surplus was dropped).  min/max still go to stats. */
+int hs_dense_gemm_filter(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
+                         int64_t doc_lo, int64_t doc_hi, void* workspace, size_t workspace_bytes, const float* thr,
+                         uint64_t* cand, int32_t cand_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream);
 
 /* K1  BM25.score_batch (bm25.py:83-127) for B queries over the CSR: query b owns tokens
  *     q_off[b]..q_off[b+1]-1 (known terms only, query order, duplicates kept) with their float64 idf
@@ -133,6 +145,12 @@ int hs_bm25_score_docs(const hs_index* idx, const int32_t* q_terms, const double
                        const int32_t* q_off, int32_t B, const int64_t* doc_ids, int32_t C, double* out,
                        void* stream);
 
+/* BM25Plus.score (bm25.py:161-179) for selected docs: idf * (num / den + delta) per known query token,
+ * tf = 0 included; same arguments as hs_bm25_score_docs plus delta */
+int hs_bm25plus_score_docs(const hs_index* idx, const int32_t* q_terms, const double* q_idf,
+                           const int32_t* q_off, int32_t B, const int64_t* doc_ids, int32_t C, double delta,
+                           double* out, void* stream);
+
 /* K3+K4  normalize_scores + weighted fusion (utils.py:57-71, core.py:264-268, pipelines.py:331-340)
  *     fused into the top-k select (core.py:271, bm25.py:141, pipelines.py:342-343): per-CTA partial
  *     top-k lists into `workspace`, then one merge.  a, b: float32 [B, n_docs] (b may be NULL when
@@ -144,6 +162,18 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
                  const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
                  const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
                  void* stream);
+/* top_k_indices (utils.py:74-87) of a float32 [B, n] array with row stride ld that is not a whole shard (e.g. the
+ * sample block of the filtered tensor-core scan): keys carry doc_base + position */
+int hs_topk_select(const float* x, int64_t n, int64_t ld, int64_t doc_base, int32_t B, int32_t k, void* workspace,
+                   size_t workspace_bytes, uint64_t* out_keys, void* stream);
+/* thr[b] = score of the kth best key of keys [B, k] (-inf when the list holds fewer than kth keys) */
+int hs_keys_kth_score(const uint64_t* keys, int32_t B, int32_t k, int32_t kth, float* thr, void* stream);
+/* candidate lists of hs_dense_gemm_filter (+ n_extra keys per query from elsewhere) -> the best k_sel by cosine,
+ * re-keyed with the fused score under the FINAL stats (HS_FUSE_SEARCHER, lexical weight 0; HS_FUSE_RAW keeps the
+ * cosine) and sorted: out_keys [B, k_out].  *overflow is OR-ed with 1 if any candidate list overflowed. */
+int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t cand_cap, const uint64_t* extra_keys,
+                   int32_t n_extra, int32_t fuse_mode, const uint32_t* stats_enc, double w_a, int32_t B, int32_t k_sel,
+                   int32_t k_out, uint64_t* out_keys, int32_t* overflow, void* stream);
 /* C1 merge: keys uint64 [n_lists, B, k] (e.g. the all-gathered per-shard lists) -> out_keys [B, k] */
 int hs_topk_merge(const uint64_t* keys, int32_t n_lists, int32_t B, int32_t k, uint64_t* out_keys,
                   void* stream);

@@ -177,6 +177,9 @@ if __name__ == "__main__" and len(sys.argv) == 1:
     main()
 
 
+PLUS_SCORE_DOCS = [0, 1, 7, 31, 32, 199, 398, 399]
+
+
 def main_plus():
     """BM25Plus (bm25.py:150-179) on the t1_small corpus -> tests/golden/t1_small_bm25plus.npz."""
     ref = refload.load()
@@ -190,6 +193,8 @@ def main_plus():
         bm.fit(docs)
         for qi, q in enumerate(queries):
             out[f"{name}_q{qi}"] = bm.score_batch(q)
+            # BM25Plus.score (bm25.py:161-179): unrounded python floats for a few docs
+            out[f"{name}_q{qi}_score64"] = np.array([bm.score(q, d) for d in PLUS_SCORE_DOCS], np.float64)
     np.savez_compressed(os.path.join(GOLDEN, "t1_small_bm25plus.npz"), **out)
     print("bm25plus golden written", len(out))
 
@@ -202,7 +207,10 @@ T2_SPEC = dict(n_docs=60_000, vocab=100_000, dim=128)
 T2_EXTRA_QUERIES = ["t5 t5 t9", "unknownterm t1"]
 
 
-def main_t2():
+T2B_SPEC = dict(n_docs=240_000, vocab=200_000, dim=64)
+
+
+def main_t2(name="t2_60k", spec_kw=None):
     """T2 tier: the unmodified reference at a size where BM25 spans many doc tiles
     (60 k docs x 100-300 tokens, 100 k-term Zipf vocabulary, 128-d).  Full score vectors are too large to commit,
     so the fixture keeps the reference's top-100 of hybrid_bm25, the canonical top-100 of its BM25 vector, a
@@ -210,7 +218,8 @@ def main_t2():
     sampled docs -> tests/golden/t2_60k.npz (+ .json).   python -m oracle.make_golden t2"""
     import hashlib
     ref = refload.load()
-    spec = synth.SynthSpec(**T2_SPEC)
+    spec_kw = spec_kw or T2_SPEC
+    spec = synth.SynthSpec(**spec_kw)
     th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
     docs = synth.doc_texts(spec, 0, spec.n_docs, th)
     emb = synth.embeddings(spec, 0, spec.n_docs)
@@ -244,10 +253,14 @@ def main_t2():
         out[k + "cos_minmax"] = np.array([cos.min(), cos.max()], np.float32)
         out[k + "bm25_max"] = np.float32(bm.max())
         print("t2 query", qi, repr(q), "done", flush=True)
-    np.savez_compressed(os.path.join(GOLDEN, "t2_60k.npz"), **out)
-    json.dump({"spec": T2_SPEC, "queries": queries}, open(os.path.join(GOLDEN, "t2_60k.json"), "w"), indent=1)
-    print("t2 golden written")
+    np.savez_compressed(os.path.join(GOLDEN, f"{name}.npz"), **out)
+    json.dump({"spec": spec_kw, "queries": queries}, open(os.path.join(GOLDEN, f"{name}.json"), "w"), indent=1)
+    print(name, "golden written")
 
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "t2":
     main_t2()
+# 240 k docs (59 doc tiles of the BM25 kernel, 200 k-term vocabulary): the largest tier the unmodified reference
+# finishes in minutes here (fit 214 us/doc, score_batch 6 us/doc and query)   python -m oracle.make_golden t2b
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "t2b":
+    main_t2("t2_240k", T2B_SPEC)

@@ -73,14 +73,17 @@ def load_case(name: str) -> GoldenCase:
 ALL_CASES = ("t0_sample_docs", "t1_small", "t1_mid")
 
 
-def load_t2():
-    """T2 tier: 60 k-doc corpus regenerated from seeds + the reference outputs frozen by
-    ``python -m oracle.make_golden t2`` (top-k lists, hashes and samples instead of full vectors)."""
-    meta = json.load(open(os.path.join(GOLDEN_DIR, "t2_60k.json")))
-    ref = dict(np.load(os.path.join(GOLDEN_DIR, "t2_60k.npz")))
+T2_CASES = ("t2_60k", "t2_240k")
+
+
+def load_t2(name: str = "t2_60k"):
+    """T2 tier: 60 k- / 240 k-doc corpus regenerated from seeds + the reference outputs frozen by
+    ``python -m oracle.make_golden t2`` / ``t2b`` (top-k lists, hashes and samples instead of full vectors)."""
+    meta = json.load(open(os.path.join(GOLDEN_DIR, f"{name}.json")))
+    ref = dict(np.load(os.path.join(GOLDEN_DIR, f"{name}.npz")))
     spec = synth.SynthSpec(**meta["spec"])
     th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
     docs = synth.doc_texts(spec, 0, spec.n_docs, th)
     emb = synth.embeddings(spec, 0, spec.n_docs)
     q_emb = synth.query_embeddings(spec, 0, len(meta["queries"]))
-    return GoldenCase("t2_60k", docs, emb, meta["queries"], q_emb, ref, meta)
+    return GoldenCase(name, docs, emb, meta["queries"], q_emb, ref, meta)

@@ -1,0 +1,166 @@
+"""GPU tests of the tensor-core dense modes (csrc/dense_gemm.cu): 3xTF32 and bf16 tcgen05 GEMM, the
+two-query-tile pass, doc ranges, and the filter epilogue of the pure-semantic search.
+
+Tolerances: ``tf32x3`` is a float32-grade mode -- |cos - exact| <= 5e-7 absolute (the ``fp32`` CUDA-core
+mode is within 2.4e-7; the reference's own BLAS/numba cosine is only pinned to 4 ulp); ``bf16`` within
+1e-2 (north star).  The filtered search must equal the stored-matrix search of the SAME mode bit for bit.
+"""
+import numpy as np
+import pytest
+
+from oracle import hybrid_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    import hybrid_search_engine_b200 as hs
+    from hybrid_search_engine_b200 import _lib
+    _lib.load()
+    return hs
+
+
+def _dec(e):
+    e = int(e)
+    u = (e & 0x7FFFFFFF) if (e & 0x80000000) else ((~e) & 0xFFFFFFFF)
+    return np.array([u], np.uint32).view(np.float32)[0]
+
+
+def _engine(hs, v, **kw):
+    from hybrid_search_engine_b200.engine import SearchEngine
+    shard = hs.DeviceIndex("cuda:0", v.shape[0])
+    shard.set_dense(torch.from_numpy(v).cuda())
+    return SearchEngine(shard, **kw)
+
+
+@pytest.mark.parametrize("n,d,B", [(1000, 384, 5), (20000, 384, 130), (3000, 768, 40), (777, 100, 33), (4097, 130, 128),
+                                   (129, 64, 1), (50000, 384, 128)])
+def test_tf32x3_within_fp32_tolerance_of_exact(hs, n, d, B):
+    """HS_DENSE_TF32X3: one corpus pass per 128 queries at float32-grade accuracy; stats match the produced
+    vectors; zero query / zero row rules; two runs give the same bits."""
+    rng = np.random.default_rng(n + d + B)
+    v = rng.standard_normal((n, d)).astype(np.float32)
+    v[3] = 0.0
+    v[5] *= 1e-3                                           # small-norm row: relative accuracy must hold
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    if B > 1:
+        q[1] = 0.0
+    eng = _engine(hs, v, max_batch=256)
+    stats = eng._stats(B)
+    qd = eng.upload_vectors(q)
+    cos = eng.dense_scan(qd, stats, "tf32x3").cpu().numpy().copy()
+    st = stats.cpu().numpy().view(np.uint32).copy()
+    stats2 = eng._stats(B)
+    cos2 = eng.dense_scan(qd, stats2, "tf32x3").cpu().numpy()
+    assert np.array_equal(cos, cos2), "tf32x3 is not bit-for-bit reproducible"
+    worst = 0.0
+    for b in sorted({0, min(1, B - 1), B // 2, B - 1}):
+        want = orc.cosine_exact(q[b], v)
+        worst = max(worst, float(np.max(np.abs(cos[b] - want))))
+        assert _dec(st[b, 0]) == cos[b].min() and _dec(st[b, 1]) == cos[b].max()
+    print(f"tf32x3 max|cos - exact| = {worst:.3e} (n={n}, d={d}, B={B})")
+    assert worst <= 5e-7
+    if B > 1:
+        assert np.all(cos[1] == 0.0)
+    assert np.all(cos[:, 3] == 0.0)
+
+
+@pytest.mark.parametrize("n,d,B", [(20000, 384, 200), (6000, 768, 256), (5000, 100, 300)])
+def test_bf16_two_query_tiles_per_pass(hs, n, d, B):
+    """B > 128 in bf16: two 128-query tiles share every landed corpus block (one pass per 256 queries)."""
+    rng = np.random.default_rng(n + d + B)
+    v = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    eng = _engine(hs, v, max_batch=512)
+    stats = eng._stats(B)
+    cos = eng.dense_scan(eng.upload_vectors(q), stats, "bf16").cpu().numpy()
+    st = stats.cpu().numpy().view(np.uint32)
+    for b in (0, 127, 128, 129, B - 1):
+        want = orc.cosine_exact(q[b], v)
+        assert np.max(np.abs(cos[b] - want)) <= 1e-2
+        assert _dec(st[b, 0]) == cos[b].min() and _dec(st[b, 1]) == cos[b].max()
+    # the single-tile launch (first 100 queries alone) gives the same bits for those queries
+    stats1 = eng._stats(100)
+    cos1 = eng.dense_scan(eng.upload_vectors(q[:100]), stats1, "bf16").cpu().numpy()
+    assert np.array_equal(cos1, cos[:100])
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "bf16"])
+def test_gemm_doc_range_matches_full_pass(hs, mode):
+    """hs_dense_gemm over [doc_lo, doc_hi) writes exactly the columns of the full pass (ragged ends)."""
+    from hybrid_search_engine_b200 import _lib
+    from hybrid_search_engine_b200._lib import check, ptr, stream_ptr
+    rng = np.random.default_rng(9)
+    n, d, B = 9000, 96, 37
+    v = rng.standard_normal((n, d)).astype(np.float32)
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    eng = _engine(hs, v)
+    m = _lib.DENSE_MODES[mode]
+    stats = eng._stats(B)
+    qd = eng.upload_vectors(q)
+    full = eng.dense_scan(qd, stats, mode).cpu().numpy().copy()
+    lo, hi = 1234, 7777
+    out = torch.full((B, hi - lo + 5), -7.0, dtype=torch.float32, device="cuda")
+    wsp, nbytes = eng._gemm_ws(B, m)
+    st2 = eng._stats(B)
+    check(eng.lib.hs_dense_gemm(eng.shard.handle, ptr(qd), B, qd.stride(0), m, lo, hi, wsp, nbytes, ptr(out),
+                                out.stride(0), ptr(st2), stream_ptr(eng.device)), "hs_dense_gemm")
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, :hi - lo], full[:, lo:hi])
+    assert np.all(got[:, hi - lo:] == -7.0)
+    s2 = st2.cpu().numpy().view(np.uint32)
+    for b in (0, B - 1):
+        assert _dec(s2[b, 0]) == full[b, lo:hi].min() and _dec(s2[b, 1]) == full[b, lo:hi].max()
+
+
+@pytest.mark.parametrize("mode,B,k", [("bf16", 300, 100), ("tf32x3", 130, 100), ("bf16", 64, 7), ("tf32x3", 5, 300)])
+def test_filtered_semantic_search_equals_stored_matrix_search(hs, mode, B, k):
+    """The GEMM-epilogue candidate filter (no [B, n] matrix) returns the same keys as GEMM -> store -> select."""
+    from hybrid_search_engine_b200.engine import QueryBatch
+    rng = np.random.default_rng(B + k)
+    n, d = 300_000, 64
+    v = rng.standard_normal((n, d)).astype(np.float32)
+    v[1000:1100] = v[2000:2100]                           # duplicate rows: exact score ties across the corpus
+    v[17] = 0.0
+    q = rng.standard_normal((B, d)).astype(np.float32)
+    q[2] = v[1003] * 0.5                                  # best hits are a tied pair
+    eng = _engine(hs, v, max_batch=128)
+    qb = QueryBatch(vectors=q)
+    s_f, i_f = eng.search_semantic(qb, k, 0.7, dense_mode=mode, filtered=True)
+    s_f, i_f = s_f.cpu().numpy().copy(), i_f.cpu().numpy().copy()
+    s_s, i_s = eng.search_semantic(qb, k, 0.7, dense_mode=mode, filtered=False)
+    s_s, i_s = s_s.cpu().numpy(), i_s.cpu().numpy()
+    assert np.array_equal(i_f, i_s)
+    assert np.array_equal(s_f, s_s)
+    assert set(i_f[2][:2].tolist()) == {1003, 2003}
+
+
+def test_tf32x3_hybrid_ids_match_exact_up_to_near_ties(hs):
+    """hybrid_bm25 through the engine with dense_mode='tf32x3' at B=128: same top-100 as the exact mode except
+    inside groups whose fused scores differ by <= 4 ulp."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=200_000, vocab=50_000, dim=384)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, torch.device("cuda:0"))
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    B = 128
+    qb = QueryBatch(vectors=synth.query_embeddings(spec, 0, B), term_ids=synth.query_terms(spec, 0, B, th).tolist())
+    eng = SearchEngine(shard, max_batch=128)
+    s_t, i_t = eng.search_hybrid_bm25(qb, 100, 0.6, 0.4, dense_mode="tf32x3")
+    s_t, i_t = s_t.cpu().numpy().copy(), i_t.cpu().numpy().copy()
+    s_e, i_e = eng.search_hybrid_bm25(qb, 100, 0.6, 0.4, dense_mode="exact")
+    s_e, i_e = s_e.cpu().numpy(), i_e.cpu().numpy()
+    assert np.max(np.abs(s_t - s_e)) <= 1e-5 * np.max(np.abs(s_e))
+    same = 0
+    for b in range(B):
+        if np.array_equal(i_t[b], i_e[b]):
+            same += 1
+            continue
+        sc = dict(zip(i_e[b].tolist(), s_e[b].tolist()))
+        sc.update({i: s for i, s in zip(i_t[b].tolist(), s_t[b].tolist()) if i not in sc})
+        for a, c in zip(i_t[b], i_e[b]):
+            assert a == c or abs(sc[int(a)] - sc[int(c)]) <= 4 * np.spacing(np.float32(abs(sc[int(c)]))), (b, a, c)
+    print(f"tf32x3 hybrid: {same}/{B} queries with identical top-100 ids, the rest differ only inside 4-ulp ties")

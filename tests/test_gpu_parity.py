@@ -609,14 +609,15 @@ def test_bm25_batched_kernel_shapes(hs, max_len, tf_hi):
     assert np.array_equal(f.cpu().numpy()[:, 2], want.astype(np.float32).max(axis=1))      # HS_STAT_MAX_B
 
 
-def test_t2_reference_at_60k_docs(hs):
-    """T2 tier: the CUDA path against outputs of the unmodified reference on a 60 k-doc corpus (15 doc tiles;
+@pytest.mark.parametrize("t2_name", ["t2_60k", "t2_240k"])
+def test_t2_reference_at_60k_docs(hs, t2_name):
+    """T2 tier: the CUDA path against outputs of the unmodified reference on a 60 k- / 240 k-doc corpus (15 / 59 doc tiles;
     index built on the device): the whole BM25 vector bit for bit (sha256), the bm25 pipeline's top-100, and the
     hybrid_bm25 top-100 (ids up to near ties of the fused score -- the reference's cosine has no defined
     summation order -- scores within the 1e-5 relative tolerance)."""
     import hashlib
     from tests.golden_cases import load_t2
-    c = load_t2()
+    c = load_t2(t2_name)
     p = hs.create_pipeline("hybrid_bm25", index_build="device")
     p.index(c.docs, embeddings=c.emb)
     assert hashlib.sha256(np.asarray(p.bm25.doc_lengths, np.int64).tobytes()).hexdigest() == str(c.ref["doc_lengths_sha256"])

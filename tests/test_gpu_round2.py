@@ -1,0 +1,149 @@
+"""GPU parity tests added in round 2: the configurations the round-1 review found untested.
+
+* hybrid_bm25 at batch 256 through the plugin API vs the oracle (bit-exact in the ``exact`` mode)
+* a batch of 3 * max_batch queries on a shard large enough that the GPU lags the host (the pinned-staging race)
+* multi_stage with the bf16 tensor-core stage 1: ids inside near-tie groups of the exact run, recall@100
+* MMR at config-5 size (C = 1000 candidates, k = 250) vs the oracle
+* BM25Plus.score / search on the device vs the unmodified reference's goldens
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import hybrid_oracle as orc
+from tests.golden_cases import load_case
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    import hybrid_search_engine_b200 as hs
+    from hybrid_search_engine_b200 import _lib
+    _lib.load()
+    return hs
+
+
+def _synth_text_corpus(n_docs, vocab, dim, nq, min_len=20, max_len=60):
+    from hybrid_search_engine_b200 import synth
+    spec = synth.SynthSpec(n_docs=n_docs, vocab=vocab, dim=dim, min_len=min_len, max_len=max_len)
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    return (spec, synth.doc_texts(spec, 0, n_docs, th), synth.embeddings(spec, 0, n_docs),
+            synth.query_texts(spec, 0, nq, th), synth.query_embeddings(spec, 0, nq))
+
+
+def test_hybrid_bm25_batch_256_matches_oracle(hs):
+    """256 queries in one search_many call (8 sub-batches of 32): ids and float32 scores == oracle."""
+    spec, docs, emb, queries, qv = _synth_text_corpus(20_000, 5_000, 384, 256)
+    p = hs.create_pipeline("hybrid_bm25")
+    p.index(docs, embeddings=emb)
+    res = p.search_many(queries, top_k=100, query_vectors=qv)
+    ix = orc.build_index(docs, emb)
+    for qi in range(0, 256, 5):
+        ids, sc, _ = orc.search_hybrid_bm25(ix, queries[qi], qv[qi], 100)
+        assert [r["doc_id"] for r in res[qi].results] == ids.tolist(), qi
+        assert np.array_equal(np.array([r["score"] for r in res[qi].results], np.float32), sc), qi
+    # and every query equals its own single-query search (sub-batch composition does not matter)
+    for qi in (0, 31, 32, 100, 255):
+        one = p.search(queries[qi], top_k=100, query_vector=qv[qi])
+        assert [r["doc_id"] for r in one.results] == [r["doc_id"] for r in res[qi].results]
+        assert [r["score"] for r in one.results] == [r["score"] for r in res[qi].results]
+
+
+def test_batch_larger_than_max_batch_on_a_large_shard(hs):
+    """B = 3 * max_batch on a 2 M-doc shard: every sub-batch must be scored with ITS OWN terms / vectors even though
+    the host runs far ahead of the GPU (regression for staging-buffer reuse across sub-batches)."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=2_000_000, vocab=200_000, dim=128)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, torch.device("cuda:0"))
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    B, mb = 24, 8
+    qv = synth.query_embeddings(spec, 0, B)
+    qt = synth.query_terms(spec, 0, B, th).tolist()
+    eng = SearchEngine(shard, max_batch=mb, dense_mode="exact")
+    s_all, i_all = eng.search_hybrid_bm25(QueryBatch(vectors=qv, term_ids=qt), 100, 0.6, 0.4)
+    s_all, i_all = s_all.cpu().numpy().copy(), i_all.cpu().numpy().copy()
+    b_all, bi_all = eng.search_bm25(QueryBatch(term_ids=qt), 50)
+    b_all, bi_all = b_all.cpu().numpy().copy(), bi_all.cpu().numpy().copy()
+    for qi in range(B):
+        s1, i1 = eng.search_hybrid_bm25(QueryBatch(vectors=qv[qi:qi + 1], term_ids=qt[qi:qi + 1]), 100, 0.6, 0.4)
+        assert np.array_equal(i1.cpu().numpy()[0], i_all[qi]), qi
+        assert np.array_equal(s1.cpu().numpy()[0], s_all[qi]), qi
+        s2, i2 = eng.search_bm25(QueryBatch(term_ids=qt[qi:qi + 1]), 50)
+        assert np.array_equal(i2.cpu().numpy()[0], bi_all[qi]) and np.array_equal(s2.cpu().numpy()[0], b_all[qi]), qi
+
+
+def test_multi_stage_bf16_stage1(hs):
+    """multi_stage with dense_mode='bf16' (tcgen05 GEMM stage 1, filtered epilogue on a 300 k-doc shard) vs the exact
+    pipeline: stage-1 recall@100 >= 0.97, and wherever a stage-2 doc differs the exact stage-1 cosine gap explains it
+    (bf16 tolerance 1e-2); stage-2 BM25 scores of shared docs are bit-identical (float64, unrounded)."""
+    spec, docs, emb, queries, qv = _synth_text_corpus(300_000, 20_000, 64, 40, min_len=5, max_len=15)
+    reranker = type("R", (), {"rerank": staticmethod(lambda q, cand, top_k=None: cand[:top_k] if top_k else cand)})()
+    out = {}
+    for mode in ("exact", "bf16"):
+        p = hs.create_pipeline("multi_stage", dense_mode=mode, reranker=reranker, index_build="device")
+        p.index(docs, embeddings=emb)
+        eng = p.searcher.engine
+        from hybrid_search_engine_b200.engine import QueryBatch
+        _, ids1 = eng.search_semantic(QueryBatch(vectors=qv), 100, 1.0)
+        out[mode] = (ids1.cpu().numpy().copy(), p.stages_1_2(queries, query_vectors=qv))
+    ids_e, st2_e = out["exact"]
+    ids_b, st2_b = out["bf16"]
+    recall = float(np.mean([len(set(ids_e[q]) & set(ids_b[q])) / 100 for q in range(len(queries))]))
+    print(f"multi_stage bf16 stage-1 recall@100 vs exact = {recall:.4f}")
+    assert recall >= 0.97
+    for q in range(len(queries)):
+        be = {d: s for s, _, d in st2_e[q]}
+        bb = {d: s for s, _, d in st2_b[q]}
+        for d in set(be) & set(bb):
+            assert be[d] == bb[d]                     # float64 BM25.score is independent of the dense mode
+        cos = orc.cosine_exact(qv[q], emb)
+        floor = np.sort(cos)[-100]
+        for d in set(bb) - set(be):
+            # a doc only the bf16 run kept must sit within the bf16 tolerance of the exact stage-1 cut
+            assert cos[d] >= floor - 2e-2, (q, d)
+
+
+def test_mmr_config5_size_matches_oracle(hs):
+    """hs_mmr at C = 1000 candidates, k = 250, d = 384 (BASELINE config 5), two queries, vs the oracle."""
+    from hybrid_search_engine_b200.engine import SearchEngine
+    rng = np.random.default_rng(11)
+    n, d, C, k = 5000, 384, 1000, 250
+    emb = rng.standard_normal((n, d)).astype(np.float32)
+    emb[100:110] = emb[200:210]                        # duplicate rows among the candidates: similarity 1.0
+    emb[7] = 0.0
+    shard = hs.DeviceIndex("cuda:0", n)
+    shard.set_dense(torch.from_numpy(emb).cuda())
+    eng = SearchEngine(shard)
+    c1 = np.concatenate([np.arange(0, 215), rng.permutation(np.arange(300, n))[:C - 215]])   # zero row + both duplicate blocks
+    rng.shuffle(c1)
+    cand = np.stack([rng.permutation(n)[:C], c1])
+    rel = np.stack([orc.diversity_relevance(np.sort(rng.random(C))[::-1].tolist()) for _ in range(2)])
+    sel = eng.mmr(torch.from_numpy(cand).cuda(), torch.from_numpy(rel).cuda(), 0.5, k).cpu().numpy()
+    for b in range(2):
+        want = orc.mmr_select(emb[cand[b]], rel[b], 0.5, k)
+        assert sel[b].tolist() == want, b
+
+
+def test_bm25plus_score_and_search_on_device(hs):
+    """BM25Plus.score (float64, unrounded) == the unmodified reference's python floats; BM25Plus.search runs the device
+    select and equals the canonical top-k of the reference's score_batch vector."""
+    PLUS_SCORE_DOCS = [0, 1, 7, 31, 32, 199, 398, 399]          # oracle/make_golden.py
+    c = load_case("t1_small")
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "t1_small_bm25plus.npz")))
+    for name, kw in (("d1", dict(delta=1.0)), ("d05_k12", dict(k1=1.2, b=0.5, delta=0.5))):
+        bm = hs.BM25Plus(**kw)
+        bm.fit(c.docs)
+        for qi, q in enumerate(c.queries):
+            want = g[f"{name}_q{qi}_score64"]
+            got = np.array([bm.score(q, d) for d in PLUS_SCORE_DOCS], np.float64)
+            assert np.array_equal(got, want), (name, q)
+            top = bm.search(q, top_k=25)
+            ref = g[f"{name}_q{qi}"]
+            ids = orc.canonical_topk(ref, 25)
+            assert [i for i, _ in top] == ids.tolist(), (name, q)
+            assert [s for _, s in top] == [float(ref[i]) for i in ids], (name, q)

@@ -158,13 +158,14 @@ def test_edge_cases():
     assert len(orc.canonical_topk(np.array([0.1, 0.5], np.float32), 10)) == 2
 
 
-def test_t2_reference_at_60k_docs():
-    """T2 tier: the oracle against the unmodified reference on a 60 k-doc corpus (BM25 posting lists spanning many
-    doc tiles).  The BM25 vector is compared through its sha256 (bit-exact), the cosine at 2048 sampled docs
+@pytest.mark.parametrize("t2_name", ["t2_60k", "t2_240k"])
+def test_t2_reference_at_60k_docs(t2_name):
+    """T2 tier: the oracle against the unmodified reference on a 60 k-doc and a 240 k-doc corpus (BM25 posting lists
+    spanning 15 / 59 doc tiles).  The BM25 vector is compared through its sha256 (bit-exact), the cosine at 2048 sampled docs
     (4 ulp), the hybrid top-100 by ids (up to near ties) and scores."""
     import hashlib
     from tests.golden_cases import load_t2
-    c = load_t2()
+    c = load_t2(t2_name)
     ix = orc.build_index(c.docs, c.emb)
     assert hashlib.sha256(np.asarray(ix.bm25.doc_lengths, np.int64).tobytes()).hexdigest() == str(c.ref["doc_lengths_sha256"])
     assert float(ix.bm25.avg_doc_len) == float(c.ref["avg_doc_len"])
