@@ -32,6 +32,7 @@ SIGNATURES = {
     "hs_index_set_doc_stats": (C.c_int, [_vp, _vp, _f64, _f64, _f64, _vp, _u32, _u32, _vp]),
     "hs_row_norms": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp]),
     "hs_bm25_impact_table": (C.c_int, [_f64, _f64, _f64, _u32, _u32, _vp, _vp]),
+    "hs_bm25_build_hot": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "hs_stats_reset": (C.c_int, [_vp, _i32, _vp]),
     "hs_stats_decode": (C.c_int, [_vp, _vp, _i32, _vp]),
     "hs_stats_encode": (C.c_int, [_vp, _vp, _i32, _vp]),

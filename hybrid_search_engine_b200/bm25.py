@@ -19,7 +19,7 @@ from .index import DeviceIndex, LexicalStats
 
 class BM25:
     def __init__(self, k1: float = 1.5, b: float = 0.75, remove_stopwords: bool = True, *, device=None,
-                 index_build: str = "host"):
+                 index_build: str = "host", group=None):
         """``index_build`` (extension): "host" keeps the vocabulary strings (``doc_freqs`` / ``idf`` dicts as in
         the reference); "device" tokenises and builds the CSR on the GPU (index_build.py) and keeps only term
         hashes -- same scores, ~30x faster ``fit`` on large corpora; the ``doc_freqs`` / ``idf`` dicts are then
@@ -31,6 +31,11 @@ class BM25:
         self.remove_stopwords = remove_stopwords
         self._device = device
         self.index_build = index_build
+        # group (extension): torch.distributed process group -- the corpus is sharded by document over its ranks
+        # (every rank is given the SAME full document list and keeps its contiguous range); scores / rankings are
+        # identical to the unsharded index on every rank
+        self.group = group
+        self.doc_base = 0
         self.stats = LexicalStats(remove_stopwords)
         self.shard: Optional[DeviceIndex] = None
         self.engine: Optional[SearchEngine] = None
@@ -54,6 +59,8 @@ class BM25:
 
     def fit(self, documents: Sequence[str], *, shard: Optional[DeviceIndex] = None):
         """bm25.py:45-81.  ``shard``: attach to an existing device shard (the pipeline's dense one)."""
+        if self.group is not None:
+            return self._fit_sharded(documents, shard)
         if self.index_build == "device":
             return self._fit_device(documents, shard)
         st = self.stats = LexicalStats(self.remove_stopwords).fit(documents)
@@ -74,6 +81,38 @@ class BM25:
                        torch.from_numpy(st.doc_lengths.astype(np.uint32).view(np.int32)), float(st.avg_doc_len),
                        st.df, st.doc_count, self.k1, self.b)
         self.engine = SearchEngine(shard)
+
+    def _fit_sharded(self, documents: Sequence[str], shard: Optional[DeviceIndex]):
+        """Doc-sharded fit: this rank tokenises documents[lo:hi], the vocabulary / df / avgdl are merged over the
+        group (LexicalStats.merge_across), the device CSR holds this rank's postings under GLOBAL term ids."""
+        import torch.distributed as dist
+        from .parallel import shard_bounds
+        if self.index_build != "host":
+            raise NotImplementedError("group= needs index_build='host' (term identity by string across ranks)")
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        lo, hi = shard_bounds(len(documents), world, rank)
+        st = self.stats = LexicalStats(self.remove_stopwords).fit(documents[lo:hi]).merge_across(self.group)
+        self.doc_count = st.doc_count
+        self.avg_doc_len = st.avg_doc_len
+        self.doc_lengths = st.doc_lengths.tolist()
+        self.doc_base = lo
+        if st.doc_count == 0:
+            self.shard = self.engine = None
+            return
+        if not torch.cuda.is_available():
+            raise _lib.HsError("no CUDA device: BM25 scoring has no CPU fallback")
+        if shard is None:
+            dev = torch.device(self._device) if self._device is not None else \
+                torch.device("cuda", torch.cuda.current_device())
+            shard = DeviceIndex(dev, hi - lo, doc_base=lo)
+        if shard.n_docs != hi - lo or shard.doc_base != lo:
+            raise ValueError("BM25.fit: the dense shard does not cover this rank's doc range")
+        self.shard = shard
+        shard.set_bm25(torch.from_numpy(st.indptr), torch.from_numpy(st.postings.view(np.int32)),
+                       torch.from_numpy(st.local_doc_lengths.astype(np.uint32).view(np.int32)), float(st.avg_doc_len),
+                       st.df, st.doc_count, self.k1, self.b,
+                       max_dl=int(st.doc_lengths.max()) if st.doc_count else 0)
+        self.engine = SearchEngine(shard, group=self.group)
 
     def _fit_device(self, documents: Sequence[str], shard: Optional[DeviceIndex]):
         from .index_build import DeviceLexicalStats
@@ -124,8 +163,8 @@ class BM25:
             raise IndexError("list index out of range")
         eng = self.engine
         ids = torch.tensor([[doc_idx]], dtype=torch.int64, device=eng.device)
-        return float(eng.bm25_score_docs([self.stats.query_term_ids(query)], ids,
-                                         plus_delta=self._plus_delta()).cpu()[0, 0])
+        return float(eng.bm25_score_docs_global([self.stats.query_term_ids(query)], ids,
+                                                plus_delta=self._plus_delta()).cpu()[0, 0])
 
     def search_many(self, queries: Sequence[str], top_k: int = 10) -> List[List[tuple]]:
         """bm25.py:129-142 per query -> [(doc_idx, score)], canonical order (score desc, doc_idx asc)."""

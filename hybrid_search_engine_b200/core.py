@@ -92,7 +92,7 @@ class Searcher:
 
     def __init__(self, model_name: str = "all-MiniLM-L6-v2", db_path: str = "index.duckdb", use_faiss: bool = False,
                  faiss_index_path: str = "index.faiss", enable_query_memory: bool = True, *, encoder=None,
-                 device=None, dense_mode: str = "exact", lexical_scorer=None):
+                 device=None, dense_mode: str = "exact", lexical_scorer=None, group=None):
         # use_faiss=True (core.py:148-168): the rows of `faiss_index_path` (a FAISS IndexFlatIP file,
         # L2-normalised at add time) replace `vectors`; only the top min(2k, N) inner products keep their
         # score.  Not reachable from the pipelines (they construct Searcher(db_path=...)).  PARITY UNPINNED:
@@ -106,6 +106,10 @@ class Searcher:
         self._device = device
         self._dense_mode = dense_mode
         self._lexical_scorer = lexical_scorer
+        # group (extension): doc-sharded over the ranks of a torch.distributed group; every rank is given the same
+        # (docs_df, vectors) and keeps its contiguous doc range; results are identical on every rank
+        self.group = group
+        self.doc_range = (0, 0)
         self.shard: Optional[DeviceIndex] = None
         self.engine: Optional[SearchEngine] = None
         self._attached = None
@@ -127,12 +131,18 @@ class Searcher:
         dev = torch.device(self._device) if self._device is not None else torch.device("cuda", torch.cuda.current_device())
         vectors = np.ascontiguousarray(vectors, dtype=np.float32)
         n = vectors.shape[0]
-        self.shard = DeviceIndex(dev, n)
-        if n > 0:
-            self.shard.set_dense(torch.from_numpy(vectors).to(dev))
+        lo, hi = 0, n
+        if self.group is not None:
+            import torch.distributed as dist
+            from .parallel import shard_bounds
+            lo, hi = shard_bounds(n, dist.get_world_size(self.group), dist.get_rank(self.group))
+        self.doc_range = (lo, hi)
+        self.shard = DeviceIndex(dev, hi - lo, doc_base=lo)
+        if hi > lo:
+            self.shard.set_dense(torch.from_numpy(vectors[lo:hi]).to(dev))
         else:
             self.shard.dim = vectors.shape[1] if vectors.ndim == 2 else 0
-        self.engine = SearchEngine(self.shard, dense_mode=self._dense_mode)
+        self.engine = SearchEngine(self.shard, group=self.group, dense_mode=self._dense_mode)
         self._attached = key
 
     def _lexical_scorer_obj(self):
@@ -148,6 +158,17 @@ class Searcher:
     def search(self, query: str, docs_df, vectors: np.ndarray, top_k: int = 5,
                semantic_weight: Optional[float] = None, lexical_weight: Optional[float] = None,
                use_learned_weights: bool = False, *, query_vector=None) -> List[Tuple[float, str, int]]:
+        """core.py:199-285 for one query."""
+        qv = None if query_vector is None else np.asarray(query_vector, dtype=np.float32)[None, :]
+        return self.search_many([query], docs_df, vectors, top_k, semantic_weight, lexical_weight,
+                                use_learned_weights, query_vectors=qv)[0]
+
+    def search_many(self, queries: Sequence[str], docs_df, vectors: np.ndarray, top_k: int = 5,
+                    semantic_weight: Optional[float] = None, lexical_weight: Optional[float] = None,
+                    use_learned_weights: bool = False, *, query_vectors=None) -> List[List[Tuple[float, str, int]]]:
+        """``search`` for a batch (extension; the reference's batch endpoint api.py:429-445 is a serial loop): ONE dense
+        pass and one fuse / select chain for all queries, the lexical kernel once per query into rows of a device
+        matrix.  Same results as one ``search`` per query."""
         if use_learned_weights:
             raise NotImplementedError("learned weights need QueryMemory/DuckDB (core.py:224-226): out of scope")
         semantic_weight = semantic_weight if semantic_weight is not None else 0.7
@@ -163,32 +184,46 @@ class Searcher:
         self.attach(docs_df, self._faiss_rows if use_faiss else vectors)
         # column lists are materialised once per docs_df object (they also key the lexical scorer's device copy)
         if self._doc_lists is None or self._doc_lists[0] is not docs_df:
-            self._doc_lists = (docs_df, docs_df["content"].to_list(), docs_df["doc_id"].to_list())
-        _, docs, doc_ids = self._doc_lists
+            docs_all = docs_df["content"].to_list()
+            lo, hi = self.doc_range
+            local = docs_all if (lo, hi) == (0, len(docs_all)) else docs_all[lo:hi]
+            self._doc_lists = (docs_df, docs_all, docs_df["doc_id"].to_list(), local)
+        _, docs, doc_ids, local_docs = self._doc_lists
         n = len(docs)
         if n == 0:
             # utils.py:67 on an empty array
             raise ValueError("zero-size array to reduction operation minimum which has no identity")
-        if query_vector is None:
+        B = len(queries)
+        if query_vectors is None:
             if self.model is None:
                 self.model = default_encoder()
-            query_vector = self.model.encode([query])[0]
-        q = np.asarray(query_vector, dtype=np.float32)[None, :]
+            query_vectors = self.model.encode(list(queries))
+        q = np.asarray(query_vectors, dtype=np.float32).reshape(B, -1)
         k = min(int(top_k), n) if top_k >= 0 else max(n + int(top_k), 0)
-        if k == 0:
-            return []
+        if k == 0 or B == 0:
+            return [[] for _ in range(B)]
         eng = self.engine
         if use_faiss:
-            lex = None
-            if lexical_weight != 0.0:
-                lex = self._lexical_scorer_obj().scores_device(query, docs)[None, :]
-            sc, ids = eng.search_faiss_style(QueryBatch(vectors=q), lex, k, semantic_weight, lexical_weight)
-        elif lexical_weight == 0.0:
+            out = []
+            for b in range(B):                                  # faiss-style retrieval is per query (not a pipeline path)
+                lex = None
+                if lexical_weight != 0.0:
+                    lex = self._lexical_scorer_obj().scores_device(queries[b], local_docs)[None, :]
+                sc, ids = eng.search_faiss_style(QueryBatch(vectors=q[b:b + 1]), lex, k, semantic_weight, lexical_weight)
+                out.append((sc.cpu().numpy()[0], ids.cpu().numpy()[0]))
+            return [[(float(s), docs[int(i)], doc_ids[int(i)]) for s, i in zip(sc, ids) if i >= 0] for sc, ids in out]
+        if lexical_weight == 0.0:
             # lex_norm * 0.0 == +0.0 for every finite lexical vector (core.py:268): skip computing it
             sc, ids = eng.search_semantic(QueryBatch(vectors=q), k, semantic_weight)
+            sc, ids = sc.cpu().numpy(), ids.cpu().numpy()
         else:
-            # device-resident lexical vector; the stored list object keys the scorer's cache
-            lex = self._lexical_scorer_obj().scores_device(query, docs)
-            sc, ids = eng.search_searcher(QueryBatch(vectors=q), lex[None, :], k, semantic_weight, lexical_weight)
-        sc, ids = sc.cpu().numpy()[0], ids.cpu().numpy()[0]
-        return [(float(s), docs[int(i)], doc_ids[int(i)]) for s, i in zip(sc, ids) if i >= 0]
+            # lexical vectors are per query and [B, n] float32: bound the device matrix by chunking the batch
+            step = max(1, min(B, (1 << 28) // max(len(local_docs), 1)))
+            parts = []
+            for s in range(0, B, step):
+                lex = self._lexical_scorer_obj().scores_device_many(queries[s:s + step], local_docs)
+                a, b_ = eng.search_searcher(QueryBatch(vectors=q[s:s + step]), lex, k, semantic_weight, lexical_weight)
+                parts.append((a.cpu().numpy(), b_.cpu().numpy()))
+            sc = np.concatenate([p[0] for p in parts])
+            ids = np.concatenate([p[1] for p in parts])
+        return [[(float(s), docs[int(i)], doc_ids[int(i)]) for s, i in zip(sc[b], ids[b]) if i >= 0] for b in range(B)]

@@ -51,6 +51,10 @@ struct Bm25Params {
     int64_t* ranges;      // [n_tokens, n_tiles + 1] posting offsets at every tile boundary (workspace)
     int n_tiles;
     double delta;         // BM25Plus only (bm25.py:150-179)
+    // hot terms (df >= half the shard): their per-doc contribution idf * frac(dl, tf) as a DENSE float64 vector, built
+    // once per index (hs_bm25_build_hot).  The batched kernel streams it like a posting chunk and adds it slot by slot
+    const double* hot_c;         // [n_hot, n_docs]; 0.0 where the doc does not hold the term
+    const int32_t* hot_of_term;  // [n_terms] -> row of hot_c, or -1
 };
 
 // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (dl / avgdl))), or 0 where the reference adds 0 (den <= 0):
@@ -255,11 +259,12 @@ constexpr int kChunkB = kBThreads * kDepth;     // 2048 postings
 constexpr int kMaxQpc = 8;                     // queries per work item
 constexpr int kTokWindow = 32;                 // query tokens whose slice bounds are staged at once (one per lane)
 
+constexpr int kDenseFlag = 0x100;              // ChunkDesc.tok bit: the chunk is a slice of a hot term's dense vector
 struct __align__(16) ChunkDesc {
-    int64_t off;                               // first posting of the chunk
+    int64_t off;                               // first posting of the chunk (dense: first element of hot_c)
     int32_t len;                               // 1 .. kChunkB
-    int16_t tok, bq;                           // token (window relative) and query (CTA relative) it belongs to
-};
+    int16_t tok, bq;                           // token (window relative; | kDenseFlag | chunk index << 9 when dense)
+};                                             // and query (CTA relative) it belongs to
 
 struct BatchSmem {
     double acc[kTileDocs + 2];                 // + a dummy slot that absorbs the padding of partial chunks
@@ -381,8 +386,11 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
         };
         // A chunk is loaded and consumed by one of three group-uniform code paths: full (kChunkB postings, no
         // predicates at all), short (<= kBThreads postings: one predicated slot) or general.
-        auto load_chunk = [&](int64_t off, int len, uint2 (&buf)[kDepth]) {
-            const uint2* pp = p.postings + off + tid;
+        auto load_chunk = [&](const ChunkDesc& cd, uint2 (&buf)[kDepth]) {
+            const int64_t off = cd.off;
+            const int len = cd.len;
+            // a dense chunk is 8-byte elements too: the same register pipeline carries postings and contributions
+            const uint2* pp = ((cd.tok & kDenseFlag) ? reinterpret_cast<const uint2*>(p.hot_c) : p.postings) + off + tid;
             if (len == kChunkB) {
 #pragma unroll
                 for (int u = 0; u < kDepth; ++u) buf[u] = __ldg(pp + u * kBThreads);
@@ -399,8 +407,9 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
         auto prefetch_chunk = [&](int ci) {
             if (tid == 0) {
                 const ChunkDesc d = sm.chunk[ci];
-                const uintptr_t lo = (reinterpret_cast<uintptr_t>(p.postings + d.off) + 15) & ~(uintptr_t)15;
-                const uintptr_t hi = reinterpret_cast<uintptr_t>(p.postings + d.off + d.len) & ~(uintptr_t)15;
+                const uint2* base = (d.tok & kDenseFlag) ? reinterpret_cast<const uint2*>(p.hot_c) : p.postings;
+                const uintptr_t lo = (reinterpret_cast<uintptr_t>(base + d.off) + 15) & ~(uintptr_t)15;
+                const uintptr_t hi = reinterpret_cast<uintptr_t>(base + d.off + d.len) & ~(uintptr_t)15;
                 if (hi > lo)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"((uint32_t)(hi - lo))
                                  : "memory");
@@ -422,7 +431,23 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
                 epilogue();
                 ++bq;
             }
-            const double idf = sm.idf[d.tok];
+            if (d.tok & kDenseFlag) {
+                // hot term: buf holds float64 contributions of consecutive docs -- slot = chunk base + tid + u * 256,
+                // conflict-free read-modify-write, no row lookup, no impact gather (x + 0.0 == x: docs without the
+                // term keep their bits)
+                const uint32_t a0 = (uint32_t)__cvta_generic_to_shared(sm.acc) + (uint32_t)(((d.tok >> 9) & 1) * kChunkB + tid) * 8u;
+#pragma unroll
+                for (int u = 0; u < kDepth; ++u) {
+                    if (tid + u * kBThreads < d.len) {
+                        const uint32_t a = a0 + (uint32_t)(u * kBThreads) * 8u;
+                        const double c = __hiloint2double((int)buf[u].y, (int)buf[u].x);
+                        sts_f64(a, __dadd_rn(lds_f64(a), c));
+                    }
+                }
+                gsync();
+                return;
+            }
+            const double idf = sm.idf[d.tok & 31];
             if (d.len > kBThreads) {
                 // full chunks and padded partial ones share this path: no per-posting predicates; one slow-path
                 // test per thread (the OR of the tfs bounds their maximum)
@@ -464,11 +489,21 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
             if (warp == 0) {
                 const int t = w0 + lane;
                 int64_t lo = 0, hi = 0;
+                int dense = 0;
                 if (t < T1) {
                     const int64_t* r = p.ranges + (int64_t)t * (p.n_tiles + 1) + tile;
                     lo = r[0];
                     hi = r[1];
                     sm.idf[lane] = p.q_idf[t];
+                    if (p.hot_of_term != nullptr && hi > lo) {
+                        const int term = p.q_terms[t];
+                        const int h = (term >= 0 && term < p.n_terms) ? __ldg(p.hot_of_term + term) : -1;
+                        if (h >= 0) {                            // the tile's slice of the term's dense vector
+                            dense = kDenseFlag;
+                            lo = (int64_t)h * p.n_docs + d_lo;
+                            hi = lo + ndoc;
+                        }
+                    }
                 }
                 const int len = (int)(hi - lo);                  // <= kTileDocs: a doc occurs once per posting list
                 const int n = (len + kChunkB - 1) / kChunkB < 2 ? (len + kChunkB - 1) / kChunkB : 2;   // chunk[] holds 2 per token
@@ -484,7 +519,7 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
                     ChunkDesc d;
                     d.off = lo + (int64_t)c * kChunkB;
                     d.len = len - c * kChunkB < kChunkB ? len - c * kChunkB : kChunkB;
-                    d.tok = (int16_t)lane;
+                    d.tok = (int16_t)(lane | dense | (dense ? (c << 9) : 0));
                     d.bq = (int16_t)q;
                     sm.chunk[incl - n + c] = d;
                 }
@@ -493,15 +528,15 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
             gsync();
             const int nC = sm.n_chunks;
             uint2 A[kDepth], Bf[kDepth];
-            if (nC > 0) load_chunk(sm.chunk[0].off, sm.chunk[0].len, A);
+            if (nC > 0) load_chunk(sm.chunk[0], A);
             if (nC > 1) prefetch_chunk(1);
             for (int i = 0; i < nC; i += 2) {
                 if (i + 2 < nC) prefetch_chunk(i + 2);
-                if (i + 1 < nC) load_chunk(sm.chunk[i + 1].off, sm.chunk[i + 1].len, Bf);
+                if (i + 1 < nC) load_chunk(sm.chunk[i + 1], Bf);
                 consume(i, A);
                 if (i + 1 >= nC) break;
                 if (i + 3 < nC) prefetch_chunk(i + 3);
-                if (i + 2 < nC) load_chunk(sm.chunk[i + 2].off, sm.chunk[i + 2].len, A);
+                if (i + 2 < nC) load_chunk(sm.chunk[i + 2], A);
                 consume(i + 1, Bf);
             }
             gsync();     // the window's chunk list and idf values may be overwritten
@@ -608,6 +643,22 @@ __global__ void impact_table_kernel(double avgdl, double k1, double one_minus_b,
         table[i] = bm25_frac_compute(k1, one_minus_b, b, avgdl, k1p1, (uint32_t)(i % w), (uint32_t)(i / w));
 }
 
+// hot_c[h, doc] = idf_h * frac(dl[doc], tf) for every posting of hot term h (the row was zeroed first): exactly the
+// product the streaming path adds per posting (bm25.py:110), so both paths accumulate the same float64 values
+__global__ void bm25_hot_build_kernel(const Bm25Params p, const int32_t* __restrict__ hot_terms,
+                                      const double* __restrict__ hot_idf, double* __restrict__ hot_c) {
+    const int h = blockIdx.y;
+    const int term = hot_terms[h];
+    if (term < 0 || term >= p.n_terms) return;
+    const int64_t lo = p.indptr[term], hi = p.indptr[term + 1];
+    const double idf = hot_idf[h];
+    double* row = hot_c + (int64_t)h * p.n_docs;
+    for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 pt = __ldg(&p.postings[i]);
+        if (pt.x < (uint64_t)p.n_docs) row[pt.x] = __dmul_rn(idf, bm25_frac(p, pt.y, p.dl[pt.x]));
+    }
+}
+
 // BM25.score for selected docs (multi_stage stage 2, pipelines.py:485): one warp per (query, candidate);
 // per token a 32-ary search of the posting list for the doc, float64 accumulation in query order.
 // PLUS: BM25Plus.score (bm25.py:161-179) -- idf * (num / den + delta) for every known query token, tf = 0 included.
@@ -672,6 +723,8 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     p.ranges = nullptr;
     p.n_tiles = (int)((idx->n_docs + kTileDocs - 1) / kTileDocs);
     p.delta = 0.0;
+    p.hot_c = idx->hot_c;
+    p.hot_of_term = idx->hot_c != nullptr ? idx->hot_of_term : nullptr;
     return HS_OK;
 }
 
@@ -706,6 +759,31 @@ int hs_bm25_impact_table(double avgdl, double k1, double b, uint32_t max_dl, uin
     impact_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(avgdl, k1, 1 - b, b, k1 + 1,
                                                                                        max_dl, tf_cap, table);
     HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+
+int hs_bm25_build_hot(hs_index* idx, const int32_t* hot_terms, const double* hot_idf, int32_t n_hot,
+                      const int32_t* hot_of_term, double* hot_c, void* stream) {
+    HS_REQUIRE(idx != nullptr, "hs_bm25_build_hot: idx is null");
+    idx->hot_c = nullptr;
+    idx->hot_of_term = nullptr;
+    idx->n_hot = 0;
+    if (n_hot == 0 || idx->n_docs == 0) return HS_OK;
+    HS_REQUIRE(n_hot > 0 && n_hot <= 32767 / 2 && hot_terms != nullptr && hot_idf != nullptr && hot_of_term != nullptr &&
+                   hot_c != nullptr, "hs_bm25_build_hot: bad arguments");
+    HS_REQUIRE(((uintptr_t)hot_c & 15) == 0, "hs_bm25_build_hot: hot_c must be 16-byte aligned");
+    static const int32_t dummy_q[1] = {0};
+    Bm25Params p;
+    int rc = fill_params(idx, dummy_q, (const double*)dummy_q, dummy_q, p, "hs_bm25_build_hot");
+    if (rc != HS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    HS_CUDA(cudaMemsetAsync(hot_c, 0, (size_t)n_hot * idx->n_docs * sizeof(double), st));
+    dim3 grid(1024, (unsigned)n_hot);
+    bm25_hot_build_kernel<<<grid, 256, 0, st>>>(p, hot_terms, hot_idf, hot_c);
+    HS_LAUNCH_CHECK();
+    idx->hot_c = hot_c;
+    idx->hot_of_term = hot_of_term;
+    idx->n_hot = n_hot;
     return HS_OK;
 }
 

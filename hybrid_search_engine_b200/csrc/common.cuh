@@ -38,6 +38,10 @@ struct hs_index {
     uint32_t max_dl = 0;
     uint32_t tf_cap = 0;
     double avgdl = 0.0, k1 = 1.5, b = 0.75;
+    // hot terms: dense float64 contribution vectors [n_hot, n_docs] + term -> row map (hs_bm25_build_hot)
+    const double* hot_c = nullptr;
+    const int32_t* hot_of_term = nullptr;
+    int32_t n_hot = 0;
 };
 
 void hs_gemm_attach_f32(hs_index* idx);      // dense_gemm.cu: builds tmap_f32 (called by hs_index_set_dense)

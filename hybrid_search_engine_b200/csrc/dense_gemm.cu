@@ -143,7 +143,7 @@ struct GemmParams {
     // FILTER epilogue
     const float* thr;            // [B] keep scores >= thr[b] (null: keep everything)
     unsigned long long* cand;    // [B, cand_cap] ranking keys
-    unsigned int* cand_cnt;      // [B] appended so far (> cand_cap = overflow, the surplus is dropped)
+    unsigned int* cand_cnt;      // [B * 32] one counter per 128-byte line (appended so far; > cand_cap = overflow)
     int cand_cap;
     uint32_t doc_base;           // global id of shard-local doc 0
 };
@@ -384,7 +384,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                                     mn[mt] = fminf(mn[mt], v);
                                     mx[mt] = fmaxf(mx[mt], v);
                                     if (v >= thr[mt]) {            // rare: above the query's starting bound
-                                        const unsigned int pos = atomicAdd(p.cand_cnt + b, 1u);
+                                        const unsigned int pos = atomicAdd(p.cand_cnt + (size_t)b * HS_CAND_CNT_STRIDE, 1u);
                                         if (pos < (unsigned int)p.cand_cap)
                                             p.cand[(int64_t)b * p.cand_cap + pos] =
                                                 hs_make_key(v, p.doc_base + (uint32_t)(doc0 + c0 + j));

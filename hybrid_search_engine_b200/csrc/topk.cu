@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kThreads) cand_select_kernel(const uint64_t* _
     __shared__ Selector<KP> sel;
     const int b = blockIdx.x, tid = threadIdx.x;
     sel.init();
-    uint32_t cnt = cand_cnt[b];
+    uint32_t cnt = cand_cnt[(size_t)b * HS_CAND_CNT_STRIDE];
     if (cnt > (uint32_t)cap) {
         if (tid == 0) atomicOr(overflow, 1);
         cnt = (uint32_t)cap;

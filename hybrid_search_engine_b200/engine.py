@@ -232,12 +232,12 @@ class SearchEngine:
         """C2: global (min, max) per query across shards -- one all-reduce(MAX) of B x 4 floats."""
         if self.group is None or self.world == 1:
             return stats
-        import torch.distributed as dist
+        from .parallel import all_reduce_
         f = self._buf("stats_f", (B, 4), torch.float32)
         st = stream_ptr(self.device)
         # (-min, max, max, -min) form: one all-reduce(MAX); same arithmetic as parallel.allreduce_stats
         check(self.lib.hs_stats_to_maxform(ptr(stats), ptr(f), B, st), "hs_stats_to_maxform")
-        dist.all_reduce(f, op=dist.ReduceOp.MAX, group=self.group)
+        all_reduce_(f, "max", self.group)
         check(self.lib.hs_stats_from_maxform(ptr(f), ptr(stats), B, st), "hs_stats_from_maxform")
         self.launches += 2
         return stats
@@ -372,14 +372,15 @@ class SearchEngine:
         k_sel = 128 if k <= 100 else (512 if k <= 480 else 2048)
         S = min(max(32768, n // 64), n // 2)
         S = (S + 127) // 128 * 128
-        cap = 1 << max(12, (4 * k_sel * ((n - S + S - 1) // S)).bit_length())      # ~4-8x the expected count
+        # candidate capacity per query: 4-8x (k_sel = 128) / 2-4x (larger k_sel) the expected k_sel * (n - S) / S appends
+        cap = 1 << max(12, ((4 if k_sel == 128 else 2) * k_sel * ((n - S + S - 1) // S)).bit_length())
         st = stream_ptr(self.device)
         out_s, out_i = [], []
         with torch.cuda.device(self.device):
             qd_all = self.upload_vectors(qb.vectors)
             overflow = self._buf("cand_ovf", (1,), torch.int32)
             overflow.zero_()
-            group = self.FILTER_GROUP if k_sel == 128 else (128 if k_sel == 512 else 32)   # bounds the candidate buffers
+            group = self.FILTER_GROUP if k_sel == 128 else 256          # bounds the candidate buffers (<= 0.5 GB)
             for s in range(0, B, group):
                 e = min(B, s + group)
                 nb = e - s
@@ -397,7 +398,7 @@ class SearchEngine:
                 thr = self._buf("cand_thr", (nb,), torch.float32)
                 check(self.lib.hs_keys_kth_score(ptr(keys_s), nb, k_sel, k_sel, ptr(thr), st), "hs_keys_kth_score")
                 cand = self._buf("cand", (nb, cap), torch.int64)
-                cnt = self._buf("cand_cnt", (nb,), torch.int32)
+                cnt = self._buf("cand_cnt", (nb * 32,), torch.int32)          # HS_CAND_CNT_STRIDE
                 cnt.zero_()
                 check(self.lib.hs_dense_gemm_filter(self.shard.handle, ptr(qd), nb, qd.stride(0), m, S, n, wsp, nbytes,
                                                     ptr(thr), ptr(cand), cap, ptr(cnt), ptr(stats), st),
@@ -411,8 +412,8 @@ class SearchEngine:
                 out_s.append(sc.clone() if B > group else sc)
                 out_i.append(ids.clone() if B > group else ids)
             if self.group is not None and self.world > 1:      # every rank must take the same branch below
-                import torch.distributed as dist
-                dist.all_reduce(overflow, op=dist.ReduceOp.MAX, group=self.group)
+                from .parallel import all_reduce_
+                all_reduce_(overflow, "max", self.group)
             if int(overflow.item()) != 0:          # a candidate list overflowed: results may miss docs
                 return None
         if len(out_s) == 1:
@@ -537,6 +538,34 @@ class SearchEngine:
             self.launches += 1
         return out
 
+    def bm25_score_docs_global(self, term_ids: Sequence[Sequence[int]], doc_ids: torch.Tensor,
+                               plus_delta: Optional[float] = None) -> torch.Tensor:
+        """``bm25_score_docs`` for GLOBAL doc ids (int64 [B, C], < 0 = padding).  Doc-sharded: every rank scores the
+        candidates it owns (the others come out 0.0) and one all-reduce(SUM) of B x C doubles assembles the result --
+        exact, because exactly one rank contributes a non-zero term per entry."""
+        local = doc_ids - self.shard.doc_base
+        local = torch.where((local >= 0) & (local < self.shard.n_docs) & (doc_ids >= 0), local,
+                            torch.full_like(local, -1))
+        out = self.bm25_score_docs(term_ids, local, plus_delta=plus_delta)
+        if self.group is not None and self.world > 1:
+            from .parallel import all_reduce_
+            all_reduce_(out, "sum", self.group)
+        return out
+
+    def gather_rows_global(self, doc_ids: torch.Tensor) -> torch.Tensor:
+        """float32 [B, C, ld] rows of the dense matrix for GLOBAL doc ids (rows this rank does not hold arrive through
+        one all-reduce(SUM) of zero-filled blocks: exact).  Used to hand MMR its candidate matrix when doc-sharded."""
+        B, Cn = doc_ids.shape
+        sh = self.shard
+        local = doc_ids - sh.doc_base
+        own = (local >= 0) & (local < sh.n_docs) & (doc_ids >= 0)
+        rows = sh.vectors[torch.where(own, local, torch.zeros_like(local)).reshape(-1)].view(B, Cn, sh.ld)
+        rows = rows * own.unsqueeze(-1).to(rows.dtype)
+        if self.group is not None and self.world > 1:
+            from .parallel import all_reduce_
+            all_reduce_(rows, "sum", self.group)
+        return rows
+
     def mmr(self, cand_ids: torch.Tensor, rel: torch.Tensor, lam: float, k: int) -> torch.Tensor:
         """DiversityPipeline._mmr (pipelines.py:531-569).  cand_ids int64 [B, C], rel float64 [B, C]."""
         B, Cn = cand_ids.shape
@@ -548,3 +577,37 @@ class SearchEngine:
                                   B, Cn, k, ptr(ws), nbytes, ptr(out), stream_ptr(self.device)), "hs_mmr")
             self.launches += 1
         return out
+
+    def mmr_sharded(self, doc_ids: np.ndarray, rel: np.ndarray, lam: float, k: int, chunk: int = 256) -> np.ndarray:
+        """MMR when the corpus is doc-sharded: ``doc_ids`` int64 [B, C] GLOBAL ids (-1 = padding),
+        ``rel`` float64 [B, C], the same on every rank.  Per chunk of queries the candidate rows are assembled on every
+        rank with one all-reduce (``gather_rows_global``), then the greedy selection -- independent per query -- runs
+        data-parallel: rank r takes every world-th query of the chunk; one all-reduce returns all selections to all
+        ranks.  -> int32 [B, k] positions into the candidate lists, identical to the unsharded ``mmr``."""
+        import torch.distributed as dist
+        rank = dist.get_rank(self.group)
+        B, Cn = doc_ids.shape
+        dev, sh = self.device, self.shard
+        out = torch.zeros((B, k), dtype=torch.int32, device=dev)          # selection + 1; 0 = not mine / none
+        with torch.cuda.device(dev):
+            for s in range(0, B, chunk):
+                e = min(B, s + chunk)
+                ids = torch.from_numpy(np.ascontiguousarray(doc_ids[s:e])).to(dev)
+                rows = self.gather_rows_global(ids)                        # [nb, C, ld] on every rank
+                mine = list(range(rank, e - s, self.world))
+                if not mine:
+                    continue
+                mt = torch.tensor(mine, dtype=torch.int64, device=dev)
+                sub = rows[mt].reshape(len(mine) * Cn, sh.ld)[:, :sh.dim].contiguous()
+                tmp = DeviceIndex(dev, len(mine) * Cn)
+                tmp.set_dense(sub)
+                cand = torch.arange(len(mine) * Cn, dtype=torch.int64, device=dev).view(len(mine), Cn)
+                cand = torch.where(ids[mt] >= 0, cand, torch.full_like(cand, -1))
+                r = torch.from_numpy(np.ascontiguousarray(rel[s:e][mine])).to(dev)
+                sel = SearchEngine(tmp).mmr(cand, r, lam, k)
+                out[s + mt] = sel + 1
+                self.launches += 2
+            from .parallel import all_reduce_
+            all_reduce_(out, "sum", self.group)
+        return (out - 1).cpu().numpy()
+

@@ -141,6 +141,37 @@ class DeviceIndex:
             check(self.lib.hs_index_set_doc_stats(self.handle, ptr(self.dl), float(avgdl), self.k1, self.b,
                                                   ptr(self.impact_table), self.max_dl, self.tf_cap, st),
                   "hs_index_set_doc_stats")
+            self._build_hot_terms(st)
+
+    HOT_MAX_TERMS = 32
+
+    def _build_hot_terms(self, st):
+        """Dense contribution vectors for the terms that occur in at least half of this shard's docs (the head of a
+        Zipfian vocabulary: ~20 terms carry ~85 % of the postings a query batch touches).  8 bytes per doc and term,
+        capped at HOT_MAX_TERMS terms and a quarter of the posting bytes.  HS_BM25_HOT=0 disables (A/B runs)."""
+        import os
+        self.hot_terms = self.hot_c = self.hot_of_term = None
+        n = self.n_docs
+        if os.environ.get("HS_BM25_HOT", "1") == "0" or n < 8192 or self.n_terms == 0 or self.avgdl <= 0:
+            check(self.lib.hs_bm25_build_hot(self.handle, None, None, 0, None, None, st), "hs_bm25_build_hot")
+            return
+        df_local = self.indptr[1:] - self.indptr[:-1]
+        budget = min(self.HOT_MAX_TERMS, int(self.postings.shape[0] // 4 // max(n, 1)))
+        cand = torch.nonzero(df_local * 2 >= n).flatten()
+        if budget <= 0 or cand.numel() == 0:
+            check(self.lib.hs_bm25_build_hot(self.handle, None, None, 0, None, None, st), "hs_bm25_build_hot")
+            return
+        if cand.numel() > budget:
+            cand = cand[torch.topk(df_local[cand], budget).indices]
+        cand = torch.sort(cand).values
+        H = int(cand.numel())
+        self.hot_terms = cand.to(torch.int32).contiguous()
+        idf = torch.from_numpy(self.idf_host[cand.cpu().numpy()]).to(self.device)
+        self.hot_of_term = torch.full((self.n_terms,), -1, dtype=torch.int32, device=self.device)
+        self.hot_of_term[cand] = torch.arange(H, dtype=torch.int32, device=self.device)
+        self.hot_c = torch.empty((H, n), dtype=torch.float64, device=self.device)
+        check(self.lib.hs_bm25_build_hot(self.handle, ptr(self.hot_terms), ptr(idf), H, ptr(self.hot_of_term),
+                                         ptr(self.hot_c), st), "hs_bm25_build_hot")
 
     # ------------------------------------------------------------------ persistence (checkpoint / resume)
     def save(self, path: str):
@@ -237,6 +268,50 @@ class LexicalStats:
         self.indptr = np.concatenate([[0], np.cumsum(self.df)]).astype(np.int64)
         self.postings = np.stack([pd.astype(np.uint32), tf.astype(np.uint32)], axis=1) if len(pd) else \
             np.zeros((0, 2), np.uint32)
+        return self
+
+    def merge_across(self, group):
+        """Doc-sharded ``fit``: this rank fitted ITS contiguous doc range; make the term ids, df,
+        doc count, doc lengths and avgdl corpus-global while the CSR keeps only this rank's docs (local doc ids).
+
+        Term ids come out exactly as a single-process fit over the whole corpus would assign them (first appearance,
+        ranks hold consecutive doc ranges), so ``idf`` / ``doc_freqs`` and every score are identical to the unsharded
+        index.  Host-side exchange with ``all_gather_object`` (works with gloo on CPU and with NCCL)."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        local_terms = list(self.vocab)                      # dict order == local id order
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (local_terms, self.df, self.doc_lengths), group=group)
+        gvocab: Dict[str, int] = {}
+        for terms, _, _ in gathered:
+            for t in terms:
+                gvocab.setdefault(t, len(gvocab))
+        v = len(gvocab)
+        df_g = np.zeros(v, np.int64)
+        for terms, df, _ in gathered:
+            if len(terms):
+                df_g[np.fromiter((gvocab[t] for t in terms), np.int64, len(terms))] += df
+        all_dl = np.concatenate([np.asarray(dl, np.int64) for _, _, dl in gathered])
+        n_global = int(all_dl.size)
+        # re-key the local CSR by global term id: posting slices re-ordered, doc ids stay local
+        remap = np.fromiter((gvocab[t] for t in local_terms), np.int64, len(local_terms))
+        order = np.argsort(remap, kind="stable")
+        lens = self.df[order]
+        starts = self.indptr[:-1][order]
+        total = int(lens.sum())
+        if total:
+            idx = np.repeat(starts - (np.cumsum(lens) - lens), lens) + np.arange(total, dtype=np.int64)
+            self.postings = self.postings[idx]
+        counts = np.zeros(v, np.int64)
+        counts[remap] = self.df
+        self.indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.local_doc_lengths = self.doc_lengths          # this rank's docs (device dl)
+        self.n_local = self.doc_count
+        self.vocab = gvocab
+        self.df = df_g
+        self.doc_lengths = all_dl                          # the reference's BM25.doc_lengths covers every doc
+        self.doc_count = n_global
+        self.avg_doc_len = (int(all_dl.sum()) / n_global) if n_global > 0 else 0      # bm25.py:71
         return self
 
     def query_term_ids(self, query: str) -> List[int]:

@@ -58,28 +58,46 @@ class LexicalScorer:
         self.n = len(docs)
         self._key = key
 
-    def scores_device(self, query: str, docs: Sequence[str]) -> torch.Tensor:
-        """float32 [N] on the device."""
+    def scores_device_many(self, queries: Sequence[str], docs: Sequence[str]) -> torch.Tensor:
+        """float32 [B, N] on the device: one upload of every query's code points / token ids, one kernel launch per
+        query (the pattern is a kernel parameter), one error read-back for the batch."""
         self.prepare(docs)
         dev = self.device
-        ql = query.lower()
-        if len(ql) > 512:
-            raise NotImplementedError("lexical scoring supports queries of at most 512 characters")
-        qc = np.frombuffer(ql.encode("utf-32-le"), dtype="<u4") if ql else np.zeros(0, np.uint32)
-        q_set = set(extract_tokens(ql))                                     # core.py:180
-        known = sorted(self.vocab[t] for t in q_set if t in self.vocab)
-        d_qc = torch.from_numpy(qc.astype(np.uint32).view(np.int32).copy()).to(dev) if len(qc) else \
-            torch.zeros(1, dtype=torch.int32, device=dev)
-        d_qt = torch.tensor(known or [0], dtype=torch.int32, device=dev)
-        out = torch.empty(max(self.n, 1), dtype=torch.float32, device=dev)
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        B = len(queries)
+        qcs, qts, meta = [], [], []
+        for query in queries:
+            ql = query.lower()
+            if len(ql) > 512:
+                raise NotImplementedError("lexical scoring supports queries of at most 512 characters")
+            qc = np.frombuffer(ql.encode("utf-32-le"), dtype="<u4") if ql else np.zeros(0, np.uint32)
+            q_set = set(extract_tokens(ql))                                 # core.py:180
+            known = sorted(self.vocab[t] for t in q_set if t in self.vocab)
+            meta.append((len(qc), len(known), len(q_set)))
+            qcs.append(qc.astype(np.uint32))
+            qts.append(np.asarray(known, np.int32))
+        c_off = np.concatenate([[0], np.cumsum([m[0] for m in meta])]).astype(np.int64)
+        t_off = np.concatenate([[0], np.cumsum([m[1] for m in meta])]).astype(np.int64)
+        all_c = np.concatenate(qcs + [np.zeros(1, np.uint32)]).view(np.int32)
+        all_t = np.concatenate(qts + [np.zeros(1, np.int32)])
+        d_qc = torch.from_numpy(all_c.copy()).to(dev)
+        d_qt = torch.from_numpy(all_t.copy()).to(dev)
+        out = torch.empty((B, max(self.n, 1)), dtype=torch.float32, device=dev)
+        err = torch.zeros(max(B, 1), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            check(self.lib.hs_lexical_scores(ptr(self.d_chars), ptr(self.d_off), self.n, ptr(d_qc), len(qc),
-                                             ptr(self.d_tok), ptr(self.d_toff), ptr(d_qt), len(known), len(q_set),
-                                             ptr(out), ptr(err), stream_ptr(dev)), "hs_lexical_scores")
-        if int(err.item()):
+            st = stream_ptr(dev)
+            for b, (n_c, n_t, n_set) in enumerate(meta):
+                check(self.lib.hs_lexical_scores(ptr(self.d_chars), ptr(self.d_off), self.n,
+                                                 d_qc.data_ptr() + 4 * int(c_off[b]), n_c, ptr(self.d_tok),
+                                                 ptr(self.d_toff), d_qt.data_ptr() + 4 * int(t_off[b]), n_t, n_set,
+                                                 out.data_ptr() + 4 * b * out.shape[1], err.data_ptr() + 4 * b, st),
+                      "hs_lexical_scores")
+        if B and int(err.max().item()):
             raise NotImplementedError("lexical scoring supports at most 64 distinct non-ASCII code points per pattern")
-        return out[:self.n]
+        return out[:, :self.n]
+
+    def scores_device(self, query: str, docs: Sequence[str]) -> torch.Tensor:
+        """float32 [N] on the device."""
+        return self.scores_device_many([query], docs)[0]
 
     def scores(self, query: str, docs: Sequence[str]) -> np.ndarray:
         return self.scores_device(query, docs).cpu().numpy()

@@ -26,6 +26,26 @@ def shard_bounds(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
     return min(n_docs, rank * per), min(n_docs, (rank + 1) * per)
 
 
+def _stage_on_host(t: torch.Tensor, group) -> bool:
+    """gloo moves CUDA tensors only for some collectives: with a gloo group device tensors are staged through the host
+    (the N > 1 logic can then run with several ranks on ONE GPU, which is how the 1-GPU test box covers it)."""
+    import torch.distributed as dist
+    return t.is_cuda and dist.get_backend(group) == "gloo"
+
+
+def all_reduce_(t: torch.Tensor, op: str = "sum", group=None) -> torch.Tensor:
+    """In-place all-reduce ("sum" | "max") over ``group``; NCCL on device tensors, gloo through the host."""
+    import torch.distributed as dist
+    rop = dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM
+    if _stage_on_host(t, group):
+        h = t.cpu()
+        dist.all_reduce(h, op=rop, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, op=rop, group=group)
+    return t
+
+
 def allreduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     """In place: columns 0 and 3 become the global minimum, 1 and 2 the global maximum.
 
@@ -48,7 +68,12 @@ def allgather_keys(keys: torch.Tensor, group=None, out: Optional[torch.Tensor] =
     world = dist.get_world_size(group)
     if out is None:
         out = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
-    dist.all_gather_into_tensor(out.view(-1), keys.contiguous().view(-1), group=group)
+    if _stage_on_host(keys, group):
+        h = torch.empty(out.shape, dtype=keys.dtype)
+        dist.all_gather_into_tensor(h.view(-1), keys.cpu().contiguous().view(-1), group=group)
+        out.copy_(h)
+    else:
+        dist.all_gather_into_tensor(out.view(-1), keys.contiguous().view(-1), group=group)
     return out
 
 

@@ -15,6 +15,12 @@ MiniLM inside Indexer/Searcher, indexer.py:91, core.py:134):
 * ``index(documents, source_paths=None, embeddings=None)``  precomputed document vectors
 * ``search(query, top_k, query_vector=None)``               precomputed query vector
 * ``search_many(queries, top_k, query_vectors=None)``       one batched launch chain for B queries
+* ``group=``        torch.distributed process group: the corpus is sharded by document over its ranks.  Every rank
+                    calls ``index`` / ``search`` with the SAME arguments, keeps its contiguous doc range (embedding rows
+                    + postings under corpus-global term ids / idf / avgdl) and returns the SAME, unsharded-identical
+                    results (C2 stats all-reduce + C1 top-k all-gather inside the engine)
+* ``attach_index(shard, documents, query_term_ids=...)``    serve a prebuilt ``DeviceIndex`` (``DeviceIndex.load``
+                    checkpoint or a synthetic shard) instead of calling ``index``
 """
 from __future__ import annotations
 
@@ -45,7 +51,7 @@ class BasePipeline:
     """pipelines.py:33-59.  Highlighting is outside the hot path."""
 
     def __init__(self, db_path: str = "index.duckdb", enable_highlighting: bool = False, *,
-                 encoder=None, device=None, dense_mode: str = "exact", index_build: str = "host"):
+                 encoder=None, device=None, dense_mode: str = "exact", index_build: str = "host", group=None):
         if enable_highlighting:
             raise NotImplementedError("highlighting is outside the B200 hot path (string post-processing)")
         self.db_path = db_path
@@ -57,6 +63,7 @@ class BasePipeline:
         self._device = device
         self._dense_mode = dense_mode
         self._index_build = index_build
+        self._group = group
 
     def index(self, documents: List[str], **kwargs):
         raise NotImplementedError
@@ -83,8 +90,35 @@ class BasePipeline:
         if self.vectors.ndim != 2 or self.vectors.shape[0] != len(documents):
             raise ValueError("embeddings must be [len(documents), dim]")
         self.searcher = Searcher(db_path=self.db_path, encoder=self._encoder, device=self._device,
-                                 dense_mode=self._dense_mode)
+                                 dense_mode=self._dense_mode, group=self._group)
         self.searcher.attach(self.docs_df, self.vectors)
+
+    def attach_index(self, shard, documents, *, query_term_ids=None, group=None):
+        """Serve a prebuilt device shard (extension): ``shard`` is a ``DeviceIndex`` holding the dense rows and -- for
+        the BM25 pipelines -- the CSR (``DeviceIndex.load`` checkpoint, ``synth_device.build_synthetic_shard``);
+        ``documents`` is any sequence with ``len`` and ``[i]`` covering ALL docs of the corpus (may be lazy);
+        ``query_term_ids(query) -> [term id]`` maps a query string to the shard's term ids (defaults to the
+        vocabulary of the last ``fit``).  ``group`` as in the constructor."""
+        from .engine import SearchEngine
+        group = group if group is not None else self._group
+        self._group = group
+        self.documents = documents
+        self.docs_df = DocTable.__new__(DocTable)
+        self.docs_df.contents = documents
+        self.vectors = None
+        self.searcher = Searcher(db_path=self.db_path, encoder=self._encoder, device=shard.device,
+                                 dense_mode=self._dense_mode, group=group)
+        self.searcher.shard = shard
+        self.searcher.engine = SearchEngine(shard, group=group, dense_mode=self._dense_mode)
+        self.searcher.doc_range = (shard.doc_base, shard.doc_base + shard.n_docs)
+        self.searcher._attached = (self.docs_df, None)
+        bm = getattr(self, "bm25", None)
+        if bm is not None and shard.has_bm25:
+            bm.shard, bm.engine, bm.group, bm.doc_base = shard, self.searcher.engine, group, shard.doc_base
+            bm.doc_count = shard.n_docs_global
+            bm.avg_doc_len = shard.avgdl
+            if query_term_ids is not None:
+                bm.stats = type("AttachedVocab", (), {"query_term_ids": staticmethod(query_term_ids)})()
 
     def _query_vectors(self, queries: Sequence[str], query_vectors=None) -> np.ndarray:
         if query_vectors is not None:
@@ -109,21 +143,23 @@ class BasicPipeline(BasePipeline):
         self._index_dense(documents, embeddings)
 
     def search(self, query: str, top_k: int = 5, *, query_vector=None) -> PipelineResult:
-        results = self.searcher.search(query=query, docs_df=self.docs_df, vectors=self.vectors, top_k=top_k,
-                                       semantic_weight=self.semantic_weight,
-                                       lexical_weight=self.lexical_weight, query_vector=query_vector)
-        return PipelineResult(
-            query=query,
-            results=[{"score": s, "content": c, "doc_id": d} for s, c, d in results],
-            metadata={"pipeline": "basic", "weights": {"semantic": self.semantic_weight}},
-            highlighted=None)
-
+        qv = None if query_vector is None else np.asarray(query_vector, np.float32)[None, :]
+        return self.search_many([query], top_k, query_vectors=qv)[0]
 
     def search_many(self, queries: Sequence[str], top_k: int = 5, *, query_vectors=None) -> List[PipelineResult]:
-        """One result per query (the lexical scorer is per query, the dense scan is shared by the batch
-        only through the device-resident index)."""
+        """One dense pass + one fuse / select chain for the batch; the lexical kernel runs once per query into the
+        rows of a device matrix (Searcher.search_many)."""
+        if self.searcher is None:
+            raise AttributeError("'NoneType' object has no attribute 'search'")       # pipelines.py:87
         qv = self._query_vectors(queries, query_vectors)
-        return [self.search(q, top_k, query_vector=qv[i]) for i, q in enumerate(queries)]
+        res = self.searcher.search_many(queries, self.docs_df, self.vectors, top_k=top_k,
+                                        semantic_weight=self.semantic_weight, lexical_weight=self.lexical_weight,
+                                        query_vectors=qv)
+        return [PipelineResult(
+            query=q,
+            results=[{"score": s, "content": c, "doc_id": d} for s, c, d in r],
+            metadata={"pipeline": "basic", "weights": {"semantic": self.semantic_weight}},
+            highlighted=None) for q, r in zip(queries, res)]
 
 
 # ------------------------------------------------------------------------------------------ bm25
@@ -132,7 +168,7 @@ class BM25Pipeline(BasePipeline):
 
     def __init__(self, db_path: str = "index.duckdb", k1: float = 1.5, b: float = 0.75, **ext):
         super().__init__(db_path, **ext)
-        self.bm25 = BM25(k1=k1, b=b, device=self._device, index_build=self._index_build)
+        self.bm25 = BM25(k1=k1, b=b, device=self._device, index_build=self._index_build, group=self._group)
         self.documents: List[str] = []
 
     def index(self, documents: List[str], source_paths: List[str] = None):
@@ -164,7 +200,7 @@ class HybridBM25Pipeline(BasePipeline):
         super().__init__(db_path, **ext)
         self.semantic_weight = semantic_weight
         self.bm25_weight = bm25_weight
-        self.bm25 = BM25(device=self._device, index_build=self._index_build)
+        self.bm25 = BM25(device=self._device, index_build=self._index_build, group=self._group)
         self.documents: List[str] = []
 
     def index(self, documents: List[str], source_paths: List[str] = None, *, embeddings=None):
@@ -214,7 +250,7 @@ class MultiStagePipeline(BasePipeline):
         self.stage1_k = stage1_k
         self.stage2_k = stage2_k
         self.final_k = final_k
-        self.bm25 = BM25(device=self._device, index_build=self._index_build)
+        self.bm25 = BM25(device=self._device, index_build=self._index_build, group=self._group)
         self.documents: List[str] = []
         self._reranker = reranker
 
@@ -236,7 +272,7 @@ class MultiStagePipeline(BasePipeline):
         k1 = min(self.stage1_k, n)
         _, ids1 = eng.search_semantic(QueryBatch(vectors=qv), k1, 1.0)          # stage 1: min-max cosine
         ids1 = ids1.clone()
-        bm = eng.bm25_score_docs(terms, ids1)                                    # stage 2: float64 BM25.score
+        bm = eng.bm25_score_docs_global(terms, ids1)                             # stage 2: float64 BM25.score
         ids_h, bm_h = ids1.cpu().numpy(), bm.cpu().numpy()
         contents = self.docs_df.contents
         # stable sort, descending: ties keep stage-1 rank (pipelines.py:486) -- one vectorised sort for the batch
@@ -295,24 +331,58 @@ class DiversityPipeline(BasePipeline):
         return [int(i) for i in sel if i >= 0]
 
     def search(self, query: str, top_k: int = 5, *, query_vector=None) -> PipelineResult:
-        results = self.searcher.search(query=query, docs_df=self.docs_df, vectors=self.vectors,
-                                       top_k=top_k * 4, query_vector=query_vector)
-        if not results:
-            return PipelineResult(query=query, results=[], metadata={})
-        doc_ids = [d for _, _, d in results]
-        doc_scores = np.array([s for s, _, _ in results])
-        # pipelines.py:589 in float64
-        doc_scores = (doc_scores - doc_scores.min()) / (doc_scores.max() - doc_scores.min() + 1e-8)
-        selected = self._mmr(None, doc_ids, doc_scores, top_k)
-        return PipelineResult(
-            query=query,
-            results=[{"score": results[i][0], "content": results[i][1], "doc_id": results[i][2],
-                      "diversity_rank": rank} for rank, i in enumerate(selected)],
-            metadata={"pipeline": "diversity", "lambda": self.lambda_param, "method": "mmr"})
+        qv = None if query_vector is None else np.asarray(query_vector, np.float32)[None, :]
+        return self.search_many([query], top_k, query_vectors=qv)[0]
 
     def search_many(self, queries: Sequence[str], top_k: int = 5, *, query_vectors=None) -> List[PipelineResult]:
+        """Batched diversity search: candidates for every query from ONE batched Searcher pass (default 0.7 / 0.3
+        hybrid, pipelines.py:573-578), then one ``hs_mmr`` launch over [B, C] candidates (one CTA per query).
+        Doc-sharded: retrieval is sharded (C2 + C1 in the engine), the candidate rows are assembled with one
+        all-reduce, the greedy MMR itself is data-parallel over the queries."""
+        if self.searcher is None:
+            raise AttributeError("'NoneType' object has no attribute 'search'")       # pipelines.py:573
         qv = self._query_vectors(queries, query_vectors)
-        return [self.search(q, top_k, query_vector=qv[i]) for i, q in enumerate(queries)]
+        cands = self.searcher.search_many(queries, self.docs_df, self.vectors, top_k=top_k * 4, query_vectors=qv)
+        B = len(queries)
+        Cmax = max((len(c) for c in cands), default=0)
+        k = min(int(top_k), Cmax)
+        out: List[Optional[PipelineResult]] = [None] * B
+        if Cmax == 0 or k <= 0:
+            return [PipelineResult(query=q, results=[], metadata={}) if not c else
+                    PipelineResult(query=q, results=[], metadata={"pipeline": "diversity", "lambda": self.lambda_param,
+                                                                  "method": "mmr"}) for q, c in zip(queries, cands)]
+        ids = np.full((B, Cmax), -1, np.int64)
+        rel = np.zeros((B, Cmax), np.float64)
+        for b, c in enumerate(cands):
+            if not c:
+                continue
+            sc = np.array([s for s, _, _ in c])
+            # pipelines.py:589 in float64
+            rel[b, :len(c)] = (sc - sc.min()) / (sc.max() - sc.min() + 1e-8)
+            ids[b, :len(c)] = [d for _, _, d in c]
+        sel = self._mmr_batch(ids, rel, k)
+        for b, (q, c) in enumerate(zip(queries, cands)):
+            if not c:
+                out[b] = PipelineResult(query=q, results=[], metadata={})          # pipelines.py:580-581
+                continue
+            picked = [int(i) for i in sel[b] if i >= 0][:min(int(top_k), len(c))]
+            out[b] = PipelineResult(
+                query=q,
+                results=[{"score": c[i][0], "content": c[i][1], "doc_id": c[i][2], "diversity_rank": rank}
+                         for rank, i in enumerate(picked)],
+                metadata={"pipeline": "diversity", "lambda": self.lambda_param, "method": "mmr"})
+        return out
+
+    def _mmr_batch(self, doc_ids: np.ndarray, rel: np.ndarray, k: int) -> np.ndarray:
+        """int32 [B, k] positions into each query's candidate list.  doc_ids int64 [B, C] GLOBAL ids (-1 = padding)."""
+        eng = self.searcher.engine
+        dev = eng.device
+        B, Cn = doc_ids.shape
+        if eng.world == 1:
+            local = torch.from_numpy(doc_ids).to(dev) - eng.shard.doc_base
+            local = torch.where(local >= 0, local, torch.full_like(local, -1))
+            return eng.mmr(local, torch.from_numpy(rel).to(dev), self.lambda_param, k).cpu().numpy()
+        return eng.mmr_sharded(doc_ids, rel, self.lambda_param, k)
 
 
 # ------------------------------------------------------------------------------------------ factory

@@ -141,3 +141,43 @@ def query_texts(spec: SynthSpec, lo: int, hi: int, thresholds: np.ndarray | None
 
 def query_embeddings(spec: SynthSpec, lo: int, hi: int) -> np.ndarray:
     return embeddings(spec, lo, hi, seed=spec.seed_qemb)
+
+
+class SynthVocab:
+    """Term identity of the synthetic corpus for the plugin API: the vocabulary is ``t0 .. t{V-1}`` and term ``t<i>``
+    has id ``i``, so a query STRING maps to term ids exactly as ``BM25.fit`` on the materialised texts would map it
+    (tokeniser + stop-word removal of extractor.py:15-31; ids of terms outside the vocabulary are dropped)."""
+
+    def __init__(self, spec: SynthSpec):
+        self.vocab_size = spec.vocab
+
+    def query_term_ids(self, query: str):
+        from .extractor import extract_tokens
+        out = []
+        for t in extract_tokens(query, remove_stopwords=True):
+            if len(t) > 1 and t[0] == "t" and t[1:].isdigit() and int(t[1:]) < self.vocab_size:
+                out.append(int(t[1:]))
+        return out
+
+
+class LazyDocs:
+    """``documents`` stand-in for a corpus that exists only as token ids in HBM: ``len`` and ``[i]`` (the text of doc i is
+    regenerated on demand; benchmark result dictionaries then carry real contents without 10 M strings on the host)."""
+
+    def __init__(self, spec: SynthSpec, materialise: bool = False):
+        self.spec, self.materialise = spec, materialise
+        self._th = None
+
+    def __len__(self):
+        return self.spec.n_docs
+
+    def __getitem__(self, i):
+        i = int(i)
+        if not 0 <= i < self.spec.n_docs:
+            raise IndexError(i)
+        if not self.materialise:
+            return f"<synthetic doc {i}>"
+        if self._th is None:
+            self._th = zipf_thresholds(self.spec.vocab, self.spec.zipf_s)
+        return doc_texts(self.spec, i, i + 1, self._th)[0]
+

@@ -85,6 +85,14 @@ int hs_row_norms(const float* vectors, int64_t n, int32_t dim, int64_t ld, float
 int hs_bm25_impact_table(double avgdl, double k1, double b, uint32_t max_dl, uint32_t tf_cap, double* table,
                          void* stream);
 
+/* Hot terms (optional, index time; call after hs_index_set_csr / hs_index_set_doc_stats): for n_hot terms that occur
+ * in most docs, hot_c[h, doc] = idf_h * num / den (bm25.py:107-110; 0.0 where the doc lacks the term) is materialised
+ * as a dense float64 vector [n_hot, n_docs]; hs_bm25_score then STREAMS that vector for such a term instead of
+ * gathering per posting -- same float64 addends in the same order, hence the same bits.  hot_of_term int32 [n_terms]
+ * maps a term to its row (-1 = not hot).  n_hot = 0 detaches. */
+int hs_bm25_build_hot(hs_index* idx, const int32_t* hot_terms, const double* hot_idf, int32_t n_hot,
+                      const int32_t* hot_of_term, double* hot_c, void* stream);
+
 /* ---- hot path ---------------------------------------------------------------------------------- */
 /* stats: uint32[B][4] order-preserving encodings {min_a, max_a, max_b, min_b}; reset before a batch */
 int hs_stats_reset(uint32_t* stats_enc, int32_t B, void* stream);
@@ -117,8 +125,11 @@ int hs_dense_gemm(const hs_index* idx, const float* queries, int32_t B, int64_t 
                   uint32_t* stats_enc, void* stream);
 /* the same GEMM with the select's pre-filter fused into its epilogue (pure-semantic retrieval: Searcher.search with
  * lexical weight 0, multi_stage stage 1, pipelines.py:474-481): nothing is stored; every (query, doc) cosine >=
- * thr[b] (NULL: all) is appended as a ranking key to cand[b, 0..cand_cap) with cand_cnt[b] counting the appends
- * (zero it first; > cand_cap afterwards = overflow, the surplus was dropped).  min/max still go to stats. */
+ * thr[b] (NULL: all) is appended as a ranking key to cand[b, 0..cand_cap) with cand_cnt[b * HS_CAND_CNT_STRIDE]
+ * counting the appends (uint32 [B * HS_CAND_CNT_STRIDE], one counter per 128-byte line so that the atomics of
+ * different queries never share an L2 line; zero it first; > cand_cap afterwards = overflow, the surplus was
+ * dropped).  min/max still go to stats. */
+#define HS_CAND_CNT_STRIDE 32
 int hs_dense_gemm_filter(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
                          int64_t doc_lo, int64_t doc_hi, void* workspace, size_t workspace_bytes, const float* thr,
                          uint64_t* cand, int32_t cand_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream);

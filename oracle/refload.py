@@ -3,8 +3,10 @@
 Imports ``search_engine.{bm25,utils,extractor,core,indexer,pipelines}`` straight from
 ``/root/reference`` (read-only, exists only in the dev container, never on the GPU box) so that
 ``oracle/make_golden.py`` can execute the reference's own code and freeze its outputs into
-``tests/golden/``.  Nothing in the product package, in ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` may import this file.
+``tests/golden/``.  Nothing in the product package, in ``-m gpu`` tests or ``smoke()`` may import this
+file; ``bench.py`` uses it for its CPU baseline legs only (``--impl reference`` / ``cpu_baseline_reference``),
+where it loads the same unmodified modules from the staged archive ``oracle/_ref/search_engine_ref.zip``
+(``python -m oracle.build_ref``) when ``/root/reference`` is absent, i.e. on the GPU box.
 
 The reference package ``__init__`` imports every hard dependency (``search_engine/__init__.py:7``),
 several of which are absent here (polars, duckdb, rapidfuzz, sentence_transformers).  We therefore
@@ -31,7 +33,9 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = "/root/reference"
+REFERENCE_ROOT = os.environ.get("HS_REFERENCE_ROOT", "/root/reference")
+# staged copy of the same unmodified modules for boxes without /root/reference (oracle/build_ref.py)
+STAGED_ZIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "search_engine_ref.zip")
 
 # text -> float32 vector table used by the SentenceTransformer stand-in
 EMBED_TABLE: dict = {}
@@ -43,7 +47,20 @@ PARTIAL_RATIO_FN = [lambda a, b: 0.0]
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "search_engine"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "search_engine")) or os.path.exists(STAGED_ZIP)
+
+
+def _package_dir() -> str:
+    """Directory holding the reference's ``search_engine`` modules: the read-only tree in the dev container, else
+    the staged archive unpacked into a fresh temporary directory (GPU box; used by bench.py's reference arm only)."""
+    live = os.path.join(REFERENCE_ROOT, "search_engine")
+    if os.path.isdir(live):
+        return live
+    import zipfile
+    tmp = tempfile.mkdtemp(prefix="hs_ref_")
+    with zipfile.ZipFile(STAGED_ZIP) as z:
+        z.extractall(tmp)
+    return os.path.join(tmp, "search_engine")
 
 
 class _Series:
@@ -131,7 +148,8 @@ def load():
     if _loaded:
         return types.SimpleNamespace(**_loaded)
     if not available():
-        raise RuntimeError("reference tree not present (only in the dev container)")
+        raise RuntimeError("reference tree not present (dev container) and no staged copy under oracle/_ref "
+                           "(python -m oracle.build_ref)")
     os.environ.setdefault("NUMBA_CACHE_DIR", os.path.join(tempfile.gettempdir(), "numba_ref_cache"))
 
     polars = types.ModuleType("polars")
@@ -154,7 +172,7 @@ def load():
         sys.modules.setdefault(name, mod)
 
     pkg = types.ModuleType("search_engine")
-    pkg.__path__ = [os.path.join(REFERENCE_ROOT, "search_engine")]
+    pkg.__path__ = [_package_dir()]
     sys.modules["search_engine"] = pkg
     try:
         from loguru import logger

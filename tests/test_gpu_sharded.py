@@ -108,3 +108,64 @@ def test_nccl_two_ranks(tmp_path):
         assert np.array_equal(got["ids"], ids) and np.array_equal(got["sc"], sc)
         got = np.load(tmp_path / f"bm25_rank{r}.npz")
         assert np.array_equal(got["ids"], ids2) and np.array_equal(got["sc"], sc2)
+
+
+# ---------------------------------------------------------------------- doc-sharded PLUGIN API on real text
+def _pipe_worker(rank, world, port, out_dir, backend):
+    """create_pipeline(..., group=WORLD) on the T1 corpus: every rank indexes the same documents, keeps its doc range,
+    and must return the 1-rank results.  backend 'nccl' = one GPU per rank; 'gloo' = all ranks on cuda:0 (the
+    exchange steps are staged through the host), which is how a 1-GPU box covers the N > 1 path."""
+    import pickle
+    import torch.distributed as dist
+    import hybrid_search_engine_b200 as hs
+    from tests.golden_cases import load_case
+    from tests.test_gpu_parity import TableEncoder
+    from oracle import hybrid_oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dev_i = rank if backend == "nccl" else 0
+    torch.cuda.set_device(dev_i)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev_i))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = _run_all_pipelines(hs, load_case("t1_small"), TableEncoder, orc, dist.group.WORLD, f"cuda:{dev_i}")
+    pickle.dump(out, open(os.path.join(out_dir, f"pipe{rank}.pkl"), "wb"))
+    dist.destroy_process_group()
+
+
+def _run_all_pipelines(hs, c, TableEncoder, orc, group, device):
+    table = {orc.preprocess_text(d): e for d, e in zip(c.docs, c.emb)}
+    table.update({q: e for q, e in zip(c.queries, c.q_emb)})
+    enc = TableEncoder(table, c.emb.shape[1])
+    rer = type("R", (), {"rerank": staticmethod(lambda q, cand, top_k=None: cand[:top_k] if top_k else cand)})()
+    out = {}
+    for name, kw, k in (("hybrid_bm25", {}, 50), ("bm25", {}, 30), ("multi_stage", dict(reranker=rer), 20),
+                        ("basic", {}, 25), ("diversity", {}, 7)):
+        p = hs.create_pipeline(name, encoder=enc, device=device, group=group, **kw)
+        p.index(c.docs)
+        res = p.search_many(c.queries, top_k=k)
+        out[name] = [[(r["doc_id"], float(r["score"]), r["content"]) for r in x.results] for x in res]
+        if name == "bm25":
+            out["bm25_score"] = [p.bm25.score(c.queries[0], d) for d in (0, 1, 200, 399)]
+            out["bm25_idf"] = sorted(p.bm25.idf.items())[:20]
+    return out
+
+
+def test_pipelines_doc_sharded_equal_unsharded(tmp_path):
+    """All five pipelines with group= over 2 ranks == the same pipelines on one rank, bit for bit (ids, scores,
+    contents), on real text with edge-case docs (T1 corpus)."""
+    import pickle
+    import torch.multiprocessing as mp
+    import hybrid_search_engine_b200 as hs
+    from oracle import hybrid_oracle as orc
+    from tests.golden_cases import load_case
+    from tests.test_gpu_parity import TableEncoder
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_pipe_worker, args=(2, port, str(tmp_path), backend), nprocs=2, join=True)
+    want = _run_all_pipelines(hs, load_case("t1_small"), TableEncoder, orc, None, "cuda:0")
+    for r in range(2):
+        got = pickle.load(open(tmp_path / f"pipe{r}.pkl", "rb"))
+        for name in want:
+            assert got[name] == want[name], (backend, r, name)

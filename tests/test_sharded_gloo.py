@@ -91,3 +91,47 @@ def test_shard_bounds_and_key_roundtrip():
     assert np.array_equal(di, ids) and np.array_equal(sc, np.where(s == 0, 0, s).astype(np.float32))
     order = np.argsort(k)[::-1]
     assert np.array_equal(ids[order], ids[orc.canonical_topk(s, 1000)])         # key order == canonical order
+
+
+# ---------------------------------------------------------------------- doc-sharded BM25.fit (LexicalStats.merge_across)
+def _fit_worker(rank, world, port, out_dir):
+    from hybrid_search_engine_b200.index import LexicalStats
+    from tests.golden_cases import load_case
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    docs = load_case("t1_small").docs
+    lo, hi = parallel.shard_bounds(len(docs), world, rank)
+    st = LexicalStats().fit(docs[lo:hi]).merge_across(dist.group.WORLD)
+    np.savez(os.path.join(out_dir, f"fit{rank}.npz"), terms=np.array(list(st.vocab), dtype=object), df=st.df,
+             indptr=st.indptr, postings=st.postings, dl=st.doc_lengths, local_dl=st.local_doc_lengths,
+             n=st.doc_count, avg=np.float64(st.avg_doc_len), lo=lo, hi=hi)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_fit_equals_single_process_fit(tmp_path, world):
+    """Every rank fits its doc range; after the merge the vocabulary (term ids), df, doc lengths and avgdl are those of a
+    single-process fit (== the reference's, tests/test_host_cpu.py) and the local CSR is the global CSR restricted to
+    the rank's docs with rebased doc ids."""
+    from hybrid_search_engine_b200.index import LexicalStats
+    from tests.golden_cases import load_case
+    mp.spawn(_fit_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    docs = load_case("t1_small").docs
+    full = LexicalStats().fit(docs)
+    for r in range(world):
+        g = np.load(tmp_path / f"fit{r}.npz", allow_pickle=True)
+        lo, hi = int(g["lo"]), int(g["hi"])
+        assert g["terms"].tolist() == list(full.vocab)
+        assert np.array_equal(g["df"], full.df) and np.array_equal(g["dl"], full.doc_lengths)
+        assert int(g["n"]) == full.doc_count and float(g["avg"]) == float(full.avg_doc_len)
+        assert np.array_equal(g["local_dl"], full.doc_lengths[lo:hi])
+        want_ptr, want_post = [0], []
+        for t in range(len(full.df)):
+            sl = full.postings[full.indptr[t]:full.indptr[t + 1]]
+            sl = sl[(sl[:, 0] >= lo) & (sl[:, 0] < hi)].copy()
+            sl[:, 0] -= lo
+            want_post.append(sl)
+            want_ptr.append(want_ptr[-1] + len(sl))
+        assert np.array_equal(g["indptr"], np.asarray(want_ptr))
+        assert np.array_equal(g["postings"], np.concatenate(want_post))
