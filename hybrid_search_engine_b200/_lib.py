@@ -46,7 +46,8 @@ SIGNATURES = {
     "hs_dense_gemm_filter": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i64, _vp, _sz, _vp, _vp, _i32, _vp, _vp, _vp]),
     "hs_topk_select": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _sz, _vp, _vp]),
     "hs_keys_kth_score": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
-    "hs_cand_select": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _f64, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hs_dense_gemm_filter_segments": (_i32, [_vp, _i32]),
+    "hs_cand_select": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _f64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hs_bm25_workspace_bytes": (_sz, [_i64, _i32]),
     "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25plus_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _vp, _sz, _vp, _vp, _vp]),

@@ -142,9 +142,11 @@ struct GemmParams {
     int q_resident;        // 1: whole query operand stays in smem; 0: its K blocks stream with the corpus blocks
     // FILTER epilogue
     const float* thr;            // [B] keep scores >= thr[b] (null: keep everything)
-    unsigned long long* cand;    // [B, cand_cap] ranking keys
-    unsigned int* cand_cnt;      // [B * 32] one counter per 128-byte line (appended so far; > cand_cap = overflow)
-    int cand_cap;
+    // candidates are appended WITHOUT atomics: every (query, CTA, epilogue group) owns one segment of seg_cap keys and
+    // its epilogue thread keeps the fill count in a register (an atomic per append stalled the warp ~1 us each)
+    unsigned long long* cand;    // [B, n_seg, seg_cap] ranking keys
+    unsigned int* cand_cnt;      // [B, n_seg] keys the segment's owner wanted to append (> seg_cap = overflow)
+    int seg_cap, n_seg;
     uint32_t doc_base;           // global id of shard-local doc 0
 };
 
@@ -313,6 +315,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
         const int e = (warp - 4) & 3;                             // TMEM lane quarter = warp id % 4
         const int etid = e * 32 + lane;                           // 0..127 within the epilogue group
         float inv_qn[MT], mn[MT], mx[MT], thr[MT];
+        uint32_t n_app[MT];                                       // FILTER: keys appended to this thread's segments
         bool active[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -321,6 +324,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             inv_qn[mt] = active[mt] ? __ldg(p.inv_qn + b) : 0.f;
             mn[mt] = __int_as_float(0x7f800000);
             mx[mt] = __int_as_float(0xff800000);
+            n_app[mt] = 0;
             thr[mt] = (EPI == kEpiFilter && active[mt] && p.thr != nullptr) ? __ldg(p.thr + p.b0 + b)
                                                                              : __int_as_float(0xff800000);
         }
@@ -376,7 +380,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                         __syncwarp();
                     } else {
                         if (active[mt]) {
-                            const int b = p.b0 + mt * kTileM + etid;
+                            unsigned long long* seg = p.cand + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
+                                                                (blockIdx.x * kEpiGroups + grp)) * p.seg_cap;
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 if (c0 + j < ndoc) {
@@ -384,10 +389,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                                     mn[mt] = fminf(mn[mt], v);
                                     mx[mt] = fmaxf(mx[mt], v);
                                     if (v >= thr[mt]) {            // rare: above the query's starting bound
-                                        const unsigned int pos = atomicAdd(p.cand_cnt + (size_t)b * HS_CAND_CNT_STRIDE, 1u);
-                                        if (pos < (unsigned int)p.cand_cap)
-                                            p.cand[(int64_t)b * p.cand_cap + pos] =
-                                                hs_make_key(v, p.doc_base + (uint32_t)(doc0 + c0 + j));
+                                        if (n_app[mt] < (uint32_t)p.seg_cap)
+                                            seg[n_app[mt]] = hs_make_key(v, p.doc_base + (uint32_t)(doc0 + c0 + j));
+                                        ++n_app[mt];
                                     }
                                 }
                             }
@@ -398,6 +402,12 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+        if constexpr (EPI == kEpiFilter) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                if (active[mt])
+                    p.cand_cnt[(int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg + (blockIdx.x * kEpiGroups + grp)] = n_app[mt];
         }
         if (p.stats != nullptr) {
 #pragma unroll
@@ -541,7 +551,7 @@ int dispatch_gemm(int kind, int mt, int epi, const CUtensorMap& tv, const CUtens
 
 int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t d0, int64_t d1,
              void* workspace, size_t workspace_bytes, int epi, float* cos, int64_t cos_ld, const float* thr,
-             uint64_t* cand, int32_t cand_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream, const char* who) {
+             uint64_t* cand, int32_t seg_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream, const char* who) {
     HS_REQUIRE(idx != nullptr, "%s: idx is null", who);
     HS_REQUIRE(mode == HS_DENSE_BF16 || mode == HS_DENSE_TF32X3, "%s: mode %d is not a tensor-core mode", who, mode);
     HS_REQUIRE(d0 >= 0 && d0 <= d1 && d1 <= idx->n_docs, "%s: doc range [%lld, %lld) outside the shard", who,
@@ -603,7 +613,8 @@ int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q,
         p.thr = thr;
         p.cand = (unsigned long long*)cand;
         p.cand_cnt = cand_cnt;
-        p.cand_cap = cand_cap;
+        p.seg_cap = seg_cap;
+        p.n_seg = hs_dense_gemm_filter_segments(idx, mode);
         p.doc_base = (uint32_t)idx->doc_base;
         rc = dispatch_gemm(kind, mt, epi, tv, tq, tql, p, pl.smem, idx->num_sms, st);
         if (rc != HS_OK) return rc;
@@ -658,12 +669,17 @@ int hs_dense_gemm(const hs_index* idx, const float* queries, int32_t B, int64_t 
                     nullptr, nullptr, 0, nullptr, stats_enc, stream, "hs_dense_gemm");
 }
 
+int32_t hs_dense_gemm_filter_segments(const hs_index* idx, int32_t mode) {
+    if (idx == nullptr) return 0;
+    return idx->num_sms * (mode == HS_DENSE_TF32X3 ? 1 : 2);      // one per CTA and epilogue group
+}
+
 int hs_dense_gemm_filter(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
                          int64_t doc_lo, int64_t doc_hi, void* workspace, size_t workspace_bytes, const float* thr,
-                         uint64_t* cand, int32_t cand_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream) {
-    HS_REQUIRE(cand != nullptr && cand_cnt != nullptr && cand_cap > 0, "hs_dense_gemm_filter: bad candidate buffers");
+                         uint64_t* cand, int32_t seg_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream) {
+    HS_REQUIRE(cand != nullptr && cand_cnt != nullptr && seg_cap > 0, "hs_dense_gemm_filter: bad candidate buffers");
     return gemm_run(idx, queries, B, ld_q, mode, doc_lo, doc_hi, workspace, workspace_bytes, kEpiFilter, nullptr, 0, thr,
-                    cand, cand_cap, cand_cnt, stats_enc, stream, "hs_dense_gemm_filter");
+                    cand, seg_cap, cand_cnt, stats_enc, stream, "hs_dense_gemm_filter");
 }
 
 }  // extern "C"

@@ -5,7 +5,7 @@
 // this kernel follows the same published definition as the CPU oracle (oracle/hybrid_oracle.py:
 // partial_ratio -- PARITY UNPINNED against rapidfuzz itself): the shorter string is the pattern, every
 // window of the longer string of at most the pattern's length (partial windows at both ends included)
-// is scored 200 * LCS / (len_pattern + len_window), the best window wins.
+// is scored (1 - (len_pattern + len_window - 2 * LCS) / (len_pattern + len_window)) * 100, the best window wins.
 //
 // One CTA per document.  LCS is the bit-parallel Allison-Dix / Hyyro recurrence
 //     U = V & PM[c];  V = (V + U) | (V & ~U);   LCS = #zero bits of V in the pattern's m bits
@@ -135,8 +135,12 @@ __global__ void __launch_bounds__(kThreads) lexical_kernel(const LexParams p) {
                 const uint64_t mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
                 zeros += __popcll(~V[w] & mask);
             }
-            // 200.0 * lcs / (n1 + len(w))
-            const double r = __ddiv_rn(__dmul_rn(200.0, (double)zeros), (double)(m + (hi - lo)));
+            // rapidfuzz's arithmetic: indel distance = len sum - 2 * LCS, similarity = 1 - dist / len sum, score = sim * 100
+            // (reproduces the published partial_ratio_alignment example 83.33333333333334, which 200 * LCS / len sum misses
+            // by one ulp)
+            const double lensum = (double)(m + (hi - lo));
+            const double dist = (double)(m + (hi - lo) - 2 * zeros);
+            const double r = __dmul_rn(__dsub_rn(1.0, __ddiv_rn(dist, lensum)), 100.0);
             if (r > best) best = r;
         }
     }

@@ -172,6 +172,7 @@ struct FuseParams {
     int64_t n, doc_base;
     int64_t ld;                 // row stride of a and b (elements)
     int mode, k, n_chunks;
+    int n_bound;                // blocks sampled for the starting bound (0 = none)
     float wa32, wb32;
     double wa64;
 };
@@ -247,7 +248,7 @@ __device__ __forceinline__ float fuse_score(const FuseParams& p, const FuseConst
 // exact key of each block.  The k-th largest of those maxima is attained by k DISTINCT docs, hence it is
 // a valid lower bound on the k-th best key of the whole shard -- and for k = 100 of 1024 maxima it sits
 // around the top 0.1 % of all docs, so the main pass rejects ~99.9 % of the elements with two FMAs.
-constexpr int kBoundBlocks = 1024;
+constexpr int kBoundBlocks = 1024;             // at most; smaller shards sample 512 or 256 blocks (bound_blocks_for)
 constexpr int kBoundDocs = 128;
 
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
@@ -264,8 +265,8 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 __global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParams p) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int blk = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    if (blk >= kBoundBlocks) return;
-    const int64_t stride = (p.n / kBoundBlocks) / kBoundDocs * kBoundDocs;     // >= kBoundDocs by the host check
+    if (blk >= p.n_bound) return;
+    const int64_t stride = (p.n / p.n_bound) / kBoundDocs * kBoundDocs;        // >= kBoundDocs by the host check
     const int64_t start = (int64_t)blk * stride;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
@@ -287,9 +288,9 @@ __global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParam
 __global__ void __launch_bounds__(kThreads) fuse_bound_kernel(const FuseParams p) {
     __shared__ uint64_t m[kBoundBlocks];
     const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < kBoundBlocks; i += kThreads) m[i] = p.blockmax[(int64_t)b * kBoundBlocks + i];
+    for (int i = threadIdx.x; i < p.n_bound; i += kThreads) m[i] = p.blockmax[(int64_t)b * kBoundBlocks + i];
     __syncthreads();
-    bitonic_sort_desc<kBoundBlocks>(m);
+    bitonic_sort_desc_n(m, p.n_bound);
     // selectors drop keys <= bound, and the doc that attains m[k-1] may itself be the k-th best: publish
     // one less (keys are unique integers).  0 if fewer than k blocks had a key: no bound.
     if (threadIdx.x == 0) p.gthr[b] = m[p.k - 1] > 0 ? m[p.k - 1] - 1 : 0;
@@ -519,27 +520,49 @@ __global__ void keys_kth_score_kernel(const uint64_t* __restrict__ keys, int B, 
 // score is monotone but not injective).  cnt > cap raises *overflow: the caller must redo the batch unfiltered.
 template <int KP>
 __global__ void __launch_bounds__(kThreads) cand_select_kernel(const uint64_t* __restrict__ cand,
-                                                               const uint32_t* __restrict__ cand_cnt, int cap,
+                                                               const uint32_t* __restrict__ cand_cnt, int n_seg, int cap,
                                                                const uint64_t* __restrict__ extra, int n_extra,
                                                                const FuseParams p, int k_sel, int k_out,
                                                                uint64_t* __restrict__ out, int32_t* overflow) {
     __shared__ Selector<KP> sel;
+    __shared__ int s_pre[1025];                     // exclusive prefix of the segments' fill counts (n_seg <= 1024)
     const int b = blockIdx.x, tid = threadIdx.x;
     sel.init();
-    uint32_t cnt = cand_cnt[(size_t)b * HS_CAND_CNT_STRIDE];
-    if (cnt > (uint32_t)cap) {
-        if (tid == 0) atomicOr(overflow, 1);
-        cnt = (uint32_t)cap;
+    int over = 0;
+    for (int s = tid; s < n_seg; s += kThreads) {
+        uint32_t c = cand_cnt[(int64_t)b * n_seg + s];
+        if (c > (uint32_t)cap) {
+            over = 1;
+            c = (uint32_t)cap;
+        }
+        s_pre[s + 1] = (int)c;
     }
-    const int64_t total = (int64_t)cnt + n_extra;
-    for (int64_t base = 0; base < total; base += kThreads * kItems) {
+    if (__syncthreads_or(over) && tid == 0) atomicOr(overflow, 1);
+    if (tid == 0) {
+        s_pre[0] = 0;
+        for (int s = 0; s < n_seg; ++s) s_pre[s + 1] += s_pre[s];
+    }
+    __syncthreads();
+    // flattened index i over the FILLED slots only: segment = last s with s_pre[s] <= i
+    const int filled = s_pre[n_seg];
+    const int total = filled + n_extra;
+    for (int base = 0; base < total; base += kThreads * kItems) {
         uint64_t key[kItems];
 #pragma unroll
         for (int j = 0; j < kItems; ++j) {
-            const int64_t i = base + j * kThreads + tid;
+            const int i = base + j * kThreads + tid;
             key[j] = 0;
-            if (i < (int64_t)cnt) key[j] = cand[(int64_t)b * cap + i];
-            else if (i < total) key[j] = extra[(int64_t)b * n_extra + (i - cnt)];
+            if (i < filled) {
+                int lo = 0, hi = n_seg;                       // invariant: s_pre[lo] <= i < s_pre[hi]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_pre[mid] <= i) lo = mid;
+                    else hi = mid;
+                }
+                key[j] = cand[((int64_t)b * n_seg + lo) * cap + (i - s_pre[lo])];
+            } else if (i < total) {
+                key[j] = extra[(int64_t)b * n_extra + (i - filled)];
+            }
         }
         sel.push(key, k_sel);
     }
@@ -637,8 +660,15 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
     dim3 grid((unsigned)p.n_chunks, (unsigned)B);
     // starting bound from block maxima when the shard is large enough for it to pay (see above)
     static const bool no_bound = getenv("HS_NO_BOUND") != nullptr;      // A/B switch, read once
-    if (n_docs >= (int64_t)kBoundBlocks * kBoundDocs * 4 && k <= kBoundBlocks / 2 && !no_bound) {
-        dim3 bg(kBoundBlocks / (kThreads / 32), (unsigned)B);
+    // as many sampled blocks (1024 / 512 / 256) as leave >= 2 strides of 128 docs per block and hold k twice
+    p.n_bound = 0;
+    for (int nb = kBoundBlocks; nb >= 256 && !no_bound; nb >>= 1)
+        if (n_docs >= (int64_t)nb * kBoundDocs * 2 && k <= nb / 2) {
+            p.n_bound = nb;
+            break;
+        }
+    if (p.n_bound > 0) {
+        dim3 bg((unsigned)(p.n_bound / (kThreads / 32)), (unsigned)B);
         fuse_blockmax_kernel<<<bg, kThreads, 0, st>>>(p);
         fuse_bound_kernel<<<B, kThreads, 0, st>>>(p);
         HS_LAUNCH_CHECK();
@@ -677,11 +707,11 @@ int hs_keys_kth_score(const uint64_t* keys, int32_t B, int32_t k, int32_t kth, f
     return HS_OK;
 }
 
-int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t cand_cap, const uint64_t* extra_keys,
-                   int32_t n_extra, int32_t fuse_mode, const uint32_t* stats_enc, double w_a, int32_t B, int32_t k_sel,
-                   int32_t k_out, uint64_t* out_keys, int32_t* overflow, void* stream) {
-    HS_REQUIRE(cand != nullptr && cand_cnt != nullptr && cand_cap > 0 && out_keys != nullptr && overflow != nullptr,
-               "hs_cand_select: null pointer");
+int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t n_seg, int32_t cand_cap,
+                   const uint64_t* extra_keys, int32_t n_extra, int32_t fuse_mode, const uint32_t* stats_enc, double w_a,
+                   int32_t B, int32_t k_sel, int32_t k_out, uint64_t* out_keys, int32_t* overflow, void* stream) {
+    HS_REQUIRE(cand != nullptr && cand_cnt != nullptr && cand_cap > 0 && n_seg > 0 && n_seg <= 1024 && out_keys != nullptr &&
+                   overflow != nullptr, "hs_cand_select: null pointer or n_seg out of range");
     HS_REQUIRE(B > 0 && k_out > 0 && k_out <= k_sel && k_sel <= HS_TOPK_MAX && n_extra >= 0 &&
                    (n_extra == 0 || extra_keys != nullptr),
                "hs_cand_select: bad sizes (k_out=%d k_sel=%d)", k_out, k_sel);
@@ -695,11 +725,11 @@ int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t cand_
     p.wa64 = w_a;
     cudaStream_t st = (cudaStream_t)stream;
     if (k_sel <= 128)
-        cand_select_kernel<128><<<B, kThreads, 0, st>>>(cand, cand_cnt, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
+        cand_select_kernel<128><<<B, kThreads, 0, st>>>(cand, cand_cnt, n_seg, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
     else if (k_sel <= 512)
-        cand_select_kernel<512><<<B, kThreads, 0, st>>>(cand, cand_cnt, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
+        cand_select_kernel<512><<<B, kThreads, 0, st>>>(cand, cand_cnt, n_seg, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
     else
-        cand_select_kernel<2048><<<B, kThreads, 0, st>>>(cand, cand_cnt, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
+        cand_select_kernel<2048><<<B, kThreads, 0, st>>>(cand, cand_cnt, n_seg, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
     HS_LAUNCH_CHECK();
     return HS_OK;
 }

@@ -372,8 +372,11 @@ class SearchEngine:
         k_sel = 128 if k <= 100 else (512 if k <= 480 else 2048)
         S = min(max(32768, n // 64), n // 2)
         S = (S + 127) // 128 * 128
-        # candidate capacity per query: 4-8x (k_sel = 128) / 2-4x (larger k_sel) the expected k_sel * (n - S) / S appends
-        cap = 1 << max(12, ((4 if k_sel == 128 else 2) * k_sel * ((n - S + S - 1) // S)).bit_length())
+        # candidates are appended per (CTA, epilogue group) segment: capacity 8x (k_sel = 128) / 4x (larger k_sel) the
+        # expected k_sel * (n - S) / S / n_seg appends of a segment, at least 32 keys
+        n_seg = self.lib.hs_dense_gemm_filter_segments(self.shard.handle, m)
+        expect = k_sel * ((n - S + S - 1) // S)
+        cap = max(32, 1 << ((8 if k_sel == 128 else 4) * expect // n_seg).bit_length())
         st = stream_ptr(self.device)
         out_s, out_i = [], []
         with torch.cuda.device(self.device):
@@ -397,15 +400,15 @@ class SearchEngine:
                                               ptr(keys_s), st), "hs_topk_select")
                 thr = self._buf("cand_thr", (nb,), torch.float32)
                 check(self.lib.hs_keys_kth_score(ptr(keys_s), nb, k_sel, k_sel, ptr(thr), st), "hs_keys_kth_score")
-                cand = self._buf("cand", (nb, cap), torch.int64)
-                cnt = self._buf("cand_cnt", (nb * 32,), torch.int32)          # HS_CAND_CNT_STRIDE
+                cand = self._buf("cand", (nb, n_seg, cap), torch.int64)
+                cnt = self._buf("cand_cnt", (nb, n_seg), torch.int32)
                 cnt.zero_()
                 check(self.lib.hs_dense_gemm_filter(self.shard.handle, ptr(qd), nb, qd.stride(0), m, S, n, wsp, nbytes,
                                                     ptr(thr), ptr(cand), cap, ptr(cnt), ptr(stats), st),
                       "hs_dense_gemm_filter")
                 stats = self._exchange_stats(stats, nb)
                 keys = self._buf("keys", (nb, k), torch.int64)
-                check(self.lib.hs_cand_select(ptr(cand), ptr(cnt), cap, ptr(keys_s), k_sel, HS_FUSE_SEARCHER, ptr(stats),
+                check(self.lib.hs_cand_select(ptr(cand), ptr(cnt), n_seg, cap, ptr(keys_s), k_sel, HS_FUSE_SEARCHER, ptr(stats),
                                               float(sw), nb, k_sel, k, ptr(keys), ptr(overflow), st), "hs_cand_select")
                 self.launches += 4 * self._gemm_passes(nb, m) + 7
                 sc, ids = self.unpack(self._merge_across(keys))

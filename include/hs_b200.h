@@ -125,14 +125,14 @@ int hs_dense_gemm(const hs_index* idx, const float* queries, int32_t B, int64_t 
                   uint32_t* stats_enc, void* stream);
 /* the same GEMM with the select's pre-filter fused into its epilogue (pure-semantic retrieval: Searcher.search with
  * lexical weight 0, multi_stage stage 1, pipelines.py:474-481): nothing is stored; every (query, doc) cosine >=
- * thr[b] (NULL: all) is appended as a ranking key to cand[b, 0..cand_cap) with cand_cnt[b * HS_CAND_CNT_STRIDE]
- * counting the appends (uint32 [B * HS_CAND_CNT_STRIDE], one counter per 128-byte line so that the atomics of
- * different queries never share an L2 line; zero it first; > cand_cap afterwards = overflow, the surplus was
- * dropped).  min/max still go to stats. */
-#define HS_CAND_CNT_STRIDE 32
+ * thr[b] (NULL: all) is appended as a ranking key to the query's candidate lists.  No atomics: each (CTA, epilogue
+ * group) of the persistent kernel owns one SEGMENT per query -- cand uint64 [B, n_seg, seg_cap], cand_cnt uint32
+ * [B, n_seg] = keys the segment's owner wanted to append (zero it first; > seg_cap afterwards = overflow, the surplus
+ * was dropped), n_seg = hs_dense_gemm_filter_segments().  min/max still go to stats. */
+int32_t hs_dense_gemm_filter_segments(const hs_index* idx, int32_t mode);
 int hs_dense_gemm_filter(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
                          int64_t doc_lo, int64_t doc_hi, void* workspace, size_t workspace_bytes, const float* thr,
-                         uint64_t* cand, int32_t cand_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream);
+                         uint64_t* cand, int32_t seg_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream);
 
 /* K1  BM25.score_batch (bm25.py:83-127) for B queries over the CSR: query b owns tokens
  *     q_off[b]..q_off[b+1]-1 (known terms only, query order, duplicates kept) with their float64 idf
@@ -179,12 +179,12 @@ int hs_topk_select(const float* x, int64_t n, int64_t ld, int64_t doc_base, int3
                    size_t workspace_bytes, uint64_t* out_keys, void* stream);
 /* thr[b] = score of the kth best key of keys [B, k] (-inf when the list holds fewer than kth keys) */
 int hs_keys_kth_score(const uint64_t* keys, int32_t B, int32_t k, int32_t kth, float* thr, void* stream);
-/* candidate lists of hs_dense_gemm_filter (+ n_extra keys per query from elsewhere) -> the best k_sel by cosine,
+/* candidate segments of hs_dense_gemm_filter (+ n_extra keys per query from elsewhere) -> the best k_sel by cosine,
  * re-keyed with the fused score under the FINAL stats (HS_FUSE_SEARCHER, lexical weight 0; HS_FUSE_RAW keeps the
- * cosine) and sorted: out_keys [B, k_out].  *overflow is OR-ed with 1 if any candidate list overflowed. */
-int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t cand_cap, const uint64_t* extra_keys,
-                   int32_t n_extra, int32_t fuse_mode, const uint32_t* stats_enc, double w_a, int32_t B, int32_t k_sel,
-                   int32_t k_out, uint64_t* out_keys, int32_t* overflow, void* stream);
+ * cosine) and sorted: out_keys [B, k_out].  *overflow is OR-ed with 1 if any segment overflowed. */
+int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t n_seg, int32_t seg_cap,
+                   const uint64_t* extra_keys, int32_t n_extra, int32_t fuse_mode, const uint32_t* stats_enc, double w_a,
+                   int32_t B, int32_t k_sel, int32_t k_out, uint64_t* out_keys, int32_t* overflow, void* stream);
 /* C1 merge: keys uint64 [n_lists, B, k] (e.g. the all-gathered per-shard lists) -> out_keys [B, k] */
 int hs_topk_merge(const uint64_t* keys, int32_t n_lists, int32_t B, int32_t k, uint64_t* out_keys,
                   void* stream);

@@ -313,9 +313,13 @@ def _lcs_len(a: str, b: str) -> int:
 
 
 def partial_ratio(s1: str, s2: str) -> float:
-    """rapidfuzz >= 3 ``fuzz.partial_ratio`` restated from its published description
-    (PARITY UNPINNED): best ``200*LCS/(len1+len_window)`` of the shorter string against every
-    window of the longer one of at most its length, partial windows at both ends included."""
+    """rapidfuzz >= 3 ``fuzz.partial_ratio`` restated from its published description: best normalised
+    indel similarity ``(1 - (len1 + len_window - 2*LCS) / (len1 + len_window)) * 100`` of the shorter string
+    against every window of the longer one of at most its length, partial windows at both ends included.
+    The arithmetic (distance -> normalised distance -> similarity -> x 100) is rapidfuzz's own and is
+    pinned by the few known-answer vectors its public documentation carries (tests/golden/
+    rapidfuzz_published.json); the window set is NOT pinned by them -- rapidfuzz itself is not installable
+    here (PARITY UNPINNED beyond those vectors)."""
     if len(s1) > len(s2):
         s1, s2 = s2, s1
     n1, n2 = len(s1), len(s2)
@@ -324,7 +328,8 @@ def partial_ratio(s1: str, s2: str) -> float:
     best = 0.0
     for i in range(-n1 + 1, n2):
         w = s2[max(0, i):min(n2, i + n1)]
-        r = 200.0 * _lcs_len(s1, w) / (n1 + len(w))
+        lensum = n1 + len(w)
+        r = (1.0 - (lensum - 2 * _lcs_len(s1, w)) / lensum) * 100.0
         if r > best:
             best = r
     return best

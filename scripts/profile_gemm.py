@@ -1,14 +1,37 @@
-"""Small fixed workload for ncu: bf16 tcgen05 GEMM dense scan, 2 M docs x 384-d, 128 queries."""
-import os, sys, torch
+"""Small fixed workloads for ncu.   python scripts/profile_gemm.py <what> [n_docs] [dim]
+   what: filter_bf16 | filter_tf32 | store_bf16_256 | store_tf32 | hybrid_tf32 | hybrid_fp32"""
+import os, sys
+import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hybrid_search_engine_b200 import synth, synth_device
-from hybrid_search_engine_b200.engine import SearchEngine
-spec = synth.SynthSpec(n_docs=2_000_000)
-shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, "cuda:0", lexical=False)
-eng = SearchEngine(shard, max_batch=128, dense_mode="bf16")
-qd = eng.upload_vectors(synth.query_embeddings(spec, 0, 128)).clone()
-stats = eng._stats(128)
-for _ in range(4):
-    eng.dense_scan(qd, stats, "bf16")
+from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+
+what = sys.argv[1]
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4_000_000
+dim = int(sys.argv[3]) if len(sys.argv) > 3 else 384
+spec = synth.SynthSpec(n_docs=n, dim=dim)
+dev = torch.device("cuda:0")
+shard = synth_device.build_synthetic_shard(spec, 0, n, dev, lexical=what.startswith("hybrid"))
+th = synth.zipf_thresholds(spec.vocab)
+reps = 3
+if what.startswith("filter"):
+    mode, B = ("bf16", 256) if what == "filter_bf16" else ("tf32x3", 128)
+    eng = SearchEngine(shard, max_batch=256, dense_mode=mode)
+    qb = QueryBatch(vectors=synth.query_embeddings(spec, 0, B))
+    for _ in range(reps):
+        eng.search_semantic(qb, 100, 1.0, filtered=True)
+elif what.startswith("store"):
+    mode, B = ("bf16", 256) if what == "store_bf16_256" else ("tf32x3", 128)
+    eng = SearchEngine(shard, max_batch=256, dense_mode=mode)
+    qd = eng.upload_vectors(synth.query_embeddings(spec, 0, B)).clone()
+    stats = eng._stats(B)
+    for _ in range(reps):
+        eng.dense_scan(qd, stats)
+else:
+    mode, B = ("tf32x3", 128) if what == "hybrid_tf32" else ("fp32", 8)
+    eng = SearchEngine(shard, max_batch=B, dense_mode=mode)
+    qb = QueryBatch(vectors=synth.query_embeddings(spec, 0, B), term_ids=synth.query_terms(spec, 0, B, th).tolist())
+    for _ in range(reps):
+        eng.search_hybrid_bm25(qb, 100, 0.6, 0.4)
 torch.cuda.synchronize()
-print("ok")
+print("done", what, n)

@@ -42,3 +42,29 @@ def test_cuda_arm_line_has_the_contract_keys():
     for key in ("bound", "achieved", "peak", "frac", "traffic", "sm_mhz", "sm_max_mhz", "reasons", "h2d_bytes_per_step",
                 "d2h_bytes_per_step", "cores", "kind", "sample", "workload"):
         assert re.search(r'"%s"' % key, src), key
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_bench_runs_on_a_small_corpus_and_reproduces_the_committed_digest():
+    """bench.py end to end on the GPU at a size that takes seconds: one JSON line with every contract key, the
+    per-kernel rooflines, the plugin-API e2e leg, ids identical to the exact mode, and the exact-mode digest of the fixed
+    64-query batch equal to the constant in tests/golden/bench_digests.json (generated at N = 1)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--n-docs", "300000", "--vocab", "50000",
+                          "--batch", "16", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--dense-mode", "tf32x3"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert (BASE_KEYS | {"gpu_launches", "clocks", "roofline", "parity", "e2e_pipeline"}) <= set(d)
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["e2e_pipeline"]["value"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"]["same_ids_as_device_run"] and d["e2e_pipeline"]["same_ids_as_device_run"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["parity"]["sharded_digest_equal"] is True
+    assert d["parity"]["queries_with_identical_topk"] >= 0.9
+    names = [k["name"] for k in d["roofline"]["kernels"]]
+    assert len(names) == 4 and names[-1].startswith("step")
+    assert all(k["ms_per_step"] > 0 and k["alg_bytes_per_step"] > 0 for k in d["roofline"]["kernels"])

@@ -183,3 +183,16 @@ def test_t2_reference_at_60k_docs(t2_name):
         ref_full = fused.copy()
         ref_full[ref_ids] = ref_sc
         assert _near_tie_equal(ids, ref_ids, ref_full, 2e-6), q
+
+
+def test_partial_ratio_restatement_reproduces_published_rapidfuzz_values():
+    """rapidfuzz is not installable here (parity unpinned); the few known-answer values its public
+    documentation carries pin the score arithmetic of the shared restatement (distance -> normalised similarity -> x 100;
+    the docs' 83.33333333333334 differs from 200 * LCS / len sum by one ulp)."""
+    import json
+    import os
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rapidfuzz_published.json")))["vectors"]
+    assert len(vec) >= 5
+    for v in vec:
+        assert orc.partial_ratio(v["s1"], v["s2"]) == v["score"], v
+        assert orc.partial_ratio(v["s2"], v["s1"]) == v["score"], v          # symmetric in its arguments
