@@ -63,6 +63,14 @@ SIGNATURES = {
     "hs_lexical_scores": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "hs_token_flags": (C.c_int, [_vp, _i64, _vp, _vp]),
     "hs_token_hashes": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "hs_radix_sort_workspace_bytes": (_sz, [_i64]),
+    "hs_radix_sort_u64": (C.c_int, [_vp, _vp, _i64, _u32, _vp, _sz, _vp]),
+    "hs_lower_bound_i64": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "hs_scan_workspace_bytes": (_sz, [_i64]),
+    "hs_exclusive_scan_i64": (C.c_int, [_vp, _vp, _i64, _vp, _sz, _vp]),
+    "hs_rle_workspace_bytes": (_sz, [_i64]),
+    "hs_run_length_encode_u64": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hs_term_doc_freqs": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "hs_synth_embeddings": (C.c_int, [_vp, _i64, _i64, _i32, _i64, _u64, _vp]),
     "hs_synth_doc_lengths": (C.c_int, [_vp, _i64, _i64, _u64, _u32, _u32, _vp]),
     "hs_synth_token_keys": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _u64, _vp, _i32, _vp]),

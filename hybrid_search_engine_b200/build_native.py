@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhs_b200.so")
-SOURCES = ["api.cu", "dense_scan.cu", "dense_gemm.cu", "bm25.cu", "topk.cu", "mmr.cu", "lexical.cu", "tokenize.cu", "synth.cu"]
+SOURCES = ["api.cu", "dense_scan.cu", "dense_gemm.cu", "bm25.cu", "topk.cu", "mmr.cu", "lexical.cu", "tokenize.cu", "sort.cu", "synth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false"]
 

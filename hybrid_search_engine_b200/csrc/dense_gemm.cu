@@ -31,6 +31,8 @@
 // per corpus pass (+ B * n * 4 written by STORE) against HBM.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -77,6 +79,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// the same load MULTICAST to every CTA of the cluster named in `mask`: the tile lands at the same shared-memory offset
+// in each of them and each one's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row atoms 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -112,6 +127,14 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t a_desc, uint64_t 
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// commit that arrives on the mbarrier at the same offset in EVERY CTA of `mask` (a stage fed by multicast loads may only
+// be refilled once all the CTAs that received it have consumed it)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -150,7 +173,12 @@ struct GemmParams {
     uint32_t doc_base;           // global id of shard-local doc 0
 };
 
-template <int KIND, int MT, int EPI>
+// CL > 1: the kernel runs in thread-block clusters of CL CTAs and the streamed QUERY blocks -- the same for every CTA --
+// are fetched once per cluster: each CTA loads 1/CL of every query block (a slice of 128/CL rows) and TMA-multicasts it
+// to all CL CTAs, which divides the L2 -> shared-memory traffic of the query operand by CL (at two query tiles per pass
+// that operand is 2/3 of what a stage brings in, and the L2 fabric, not the tensor pipe, bounds the pass).  All CTAs of
+// a cluster run the same number of tile iterations (surplus tiles are out-of-range: TMA zero-fills, the epilogue skips).
+template <int KIND, int MT, int EPI, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_ql, const GemmParams p) {
@@ -181,11 +209,18 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.d1 - p.d0 + kTileN - 1) / kTileN;
+    // tile iterations of this CTA: tile t = blockIdx.x + i * gridDim.x.  In a cluster every CTA runs the same count
+    const int64_t n_iter = CL > 1 ? (n_tiles + gridDim.x - 1) / gridDim.x
+                                  : (n_tiles > blockIdx.x ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+    uint32_t crank = 0;
+    if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    constexpr int kSliceRows = kTileM / CL;                       // rows of a query block this CTA fetches for the cluster
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CL);          // the MMA commits of every CTA that received the stage's multicast blocks
             mbar_init(&conv[s], 128);          // every converter thread arrives
         }
         mbar_init(q_full, 1);
@@ -202,6 +237,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anything arrives on them remotely
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
@@ -217,8 +253,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                                         part == 0 ? &tmap_q : &tmap_ql, kb * kElems, mt * kTileM, q_full);
             }
             int64_t it = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int row0 = (int)(p.d0 + t * kTileN);
+            for (int64_t i = 0; i < n_iter; ++i) {
+                const int64_t t = blockIdx.x + i * gridDim.x;
+                const int row0 = (int)(p.d0 + t * kTileN);      // beyond the matrix for a surplus tile: zero fill
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
                     const int s = (int)(it % p.stages);
                     const uint32_t ph = (uint32_t)((it / p.stages) & 1);
@@ -228,9 +265,14 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                     tma_load_2d(stg, &tmap_v, kb * kElems, row0, &full[s]);
                     if (!p.q_resident) {    // query K blocks ride along (served from L2 after the first tile)
                         for (int mt = 0; mt < MT; ++mt)
-                            for (int part = 0; part < NQP; ++part)
-                                tma_load_2d(stg + V_BYTES + (mt * NQP + part) * kBlockBytes,
-                                            part == 0 ? &tmap_q : &tmap_ql, kb * kElems, mt * kTileM, &full[s]);
+                            for (int part = 0; part < NQP; ++part) {
+                                unsigned char* dst = stg + V_BYTES + (mt * NQP + part) * kBlockBytes;
+                                if constexpr (CL > 1)       // my row slice of the block, to every CTA of the cluster
+                                    tma_load_2d_mc(dst + crank * kSliceRows * 128, part == 0 ? &tmap_q : &tmap_ql, kb * kElems,
+                                                   mt * kTileM + (int)crank * kSliceRows, &full[s], kMask);
+                                else
+                                    tma_load_2d(dst, part == 0 ? &tmap_q : &tmap_ql, kb * kElems, mt * kTileM, &full[s]);
+                            }
                     }
                 }
             }
@@ -244,8 +286,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                                    ((uint32_t)(kTileM >> 4) << 24);
             if (p.q_resident) mbar_wait(q_full, 0);
-            int64_t it = 0, tile_i = 0;
-            for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_i) {
+            int64_t it = 0;
+            for (int64_t tile_i = 0; tile_i < n_iter; ++tile_i) {
                 const int buf = (int)(tile_i & 1);
                 mbar_wait(&tmem_empty[buf], (uint32_t)(((tile_i >> 1) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -278,7 +320,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                             }
                         }
                     }
-                    umma_commit(&empty[s]);                  // stage reusable once these MMAs have read it
+                    // stage reusable once these MMAs have read it (in a cluster: once EVERY CTA's MMAs have)
+                    if constexpr (CL > 1) umma_commit_mc(&empty[s], kMask);
+                    else umma_commit(&empty[s]);
                 }
                 umma_commit(&tmem_full[buf]);                // accumulators of this tile complete
             }
@@ -288,7 +332,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
         // the landed (swizzled) block into the stage's second buffer -- same addresses, so the swizzle carries over
         const int ctid = threadIdx.x - 256;                 // 0..127
         int64_t it = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int64_t i = 0; i < n_iter; ++i) {
             for (int kb = 0; kb < p.kb; ++kb, ++it) {
                 const int s = (int)(it % p.stages);
                 const uint32_t ph = (uint32_t)((it / p.stages) & 1);
@@ -330,7 +374,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
         }
         float* tr = s_tr + (warp - 4) * (32 * 33);                // per-warp 32 x 32 transpose tile (padded)
         int64_t seq = 0;                                          // tiles this group has drained
-        for (int64_t tile_i = grp; blockIdx.x + tile_i * gridDim.x < n_tiles; tile_i += kEpiGroups, ++seq) {
+        for (int64_t tile_i = grp; tile_i < n_iter; tile_i += kEpiGroups, ++seq) {
             const int64_t t = blockIdx.x + tile_i * gridDim.x;
             const int buf = (int)(tile_i & 1);
             const int64_t doc0 = p.d0 + t * kTileN;
@@ -358,18 +402,46 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)((buf * MT + mt) * kTileN + c0), r);
                     if (c0 >= ndoc || nrow == 0) continue;                  // warp-uniform
-                    if constexpr (EPI == kEpiStore) {
-                        // thread = query: scale, fold min/max, then transpose through smem so that the global
-                        // stores run along the docs of ONE query (128 contiguous bytes per instruction)
+                    // All shared-memory reads of the chunk happen BEFORE any store (the 1 / |v| values as eight 16-byte
+                    // loads into registers), and the scores are computed branch-free: a store inside the per-element loop
+                    // made the compiler keep every later load behind it (possible aliasing through generic pointers), which
+                    // serialised 256 shared-memory round trips per tile and starved the tensor pipe (12 % active).
+                    float v[32];
+                    {
+                        const float4* ivp = reinterpret_cast<const float4*>(inv_vn_tile + c0);
+                        const float qn = inv_qn[mt];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[j]) * inv_vn_tile[c0 + j] * inv_qn[mt];
-                            if (active[mt] && c0 + j < ndoc) {
-                                mn[mt] = fminf(mn[mt], v);
-                                mx[mt] = fmaxf(mx[mt], v);
-                            }
-                            tr[lane * 33 + j] = v;
+                        for (int q4 = 0; q4 < 8; ++q4) {
+                            const float4 iv = ivp[q4];
+                            v[4 * q4 + 0] = __uint_as_float(r[4 * q4 + 0]) * iv.x * qn;
+                            v[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) * iv.y * qn;
+                            v[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) * iv.z * qn;
+                            v[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) * iv.w * qn;
                         }
+                    }
+                    const int nvalid = ndoc - c0 < 32 ? ndoc - c0 : 32;    // columns of this chunk that are real docs
+                    if (active[mt]) {
+                        if (nvalid == 32) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                mn[mt] = fminf(mn[mt], v[j]);
+                                mx[mt] = fmaxf(mx[mt], v[j]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (j < nvalid) {
+                                    mn[mt] = fminf(mn[mt], v[j]);
+                                    mx[mt] = fmaxf(mx[mt], v[j]);
+                                }
+                            }
+                        }
+                    }
+                    if constexpr (EPI == kEpiStore) {
+                        // transpose through smem so that the global stores run along the docs of ONE query (128 contiguous
+                        // bytes per instruction)
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
                         __syncwarp();
                         if (c0 + lane < ndoc) {
                             float* dst = p.cos + (int64_t)(p.b0 + mt * kTileM + e * 32) * p.cos_ld + (doc0 - p.d0) + c0 + lane;
@@ -380,17 +452,17 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                         __syncwarp();
                     } else {
                         if (active[mt]) {
-                            unsigned long long* seg = p.cand + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
-                                                                (blockIdx.x * kEpiGroups + grp)) * p.seg_cap;
+                            unsigned hit = 0;                      // columns at or above the query's starting bound
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (c0 + j < ndoc) {
-                                    const float v = __uint_as_float(r[j]) * inv_vn_tile[c0 + j] * inv_qn[mt];
-                                    mn[mt] = fminf(mn[mt], v);
-                                    mx[mt] = fmaxf(mx[mt], v);
-                                    if (v >= thr[mt]) {            // rare: above the query's starting bound
+                            for (int j = 0; j < 32; ++j) hit |= (v[j] >= thr[mt] && j < nvalid) ? (1u << j) : 0u;
+                            if (hit != 0) {                        // rare
+                                unsigned long long* seg = p.cand + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
+                                                                    (blockIdx.x * kEpiGroups + grp)) * p.seg_cap;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if ((hit >> j) & 1u) {
                                         if (n_app[mt] < (uint32_t)p.seg_cap)
-                                            seg[n_app[mt]] = hs_make_key(v, p.doc_base + (uint32_t)(doc0 + c0 + j));
+                                            seg[n_app[mt]] = hs_make_key(v[j], p.doc_base + (uint32_t)(doc0 + c0 + j));
                                         ++n_app[mt];
                                     }
                                 }
@@ -423,6 +495,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
     // ------------------------------------------------ teardown
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it / arrive on it
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
@@ -476,7 +549,7 @@ EncodeTiledFn encode_fn() {
 
 // row-major [rows, ld] of bf16 (elem_bytes 2) or float32 (4) -> TMA map with a 128-byte x 128-row box, 128-byte
 // swizzle, zero fill out of bounds (K tail beyond ld, rows beyond the matrix)
-int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, int elem_bytes) {
+int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, int elem_bytes, int box_rows = 128) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         hs_set_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -484,7 +557,7 @@ int make_tmap(CUtensorMap* map, const void* base, int64_t rows, int64_t ld, int 
     }
     cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * elem_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), 128u};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -521,32 +594,71 @@ bool make_plan(int kind, int mt, int epi, int64_t ld_elems, Plan& pl) {
     return stages >= 2;
 }
 
-template <int KIND, int MT, int EPI>
+template <int KIND, int MT, int EPI, int CL>
 int launch_gemm(const CUtensorMap& tv, const CUtensorMap& tq, const CUtensorMap& tql, const GemmParams& p, size_t smem,
                 int num_sms, cudaStream_t st) {
-    auto kern = dense_gemm_kernel<KIND, MT, EPI>;
+    auto kern = dense_gemm_kernel<KIND, MT, EPI, CL>;
     static size_t smem_set[16] = {0};
     HS_CUDA(hs_smem_limit(kern, smem, smem_set));
     const int64_t n_tiles = (p.d1 - p.d0 + kTileN - 1) / kTileN;
-    const int grid = (int)(n_tiles < num_sms ? n_tiles : num_sms);
-    kern<<<grid, kThreads, smem, st>>>(tv, tq, tql, p);
-    HS_LAUNCH_CHECK();
+    int grid = (int)(n_tiles < num_sms ? n_tiles : num_sms);
+    if (CL == 1) {
+        kern<<<grid, kThreads, smem, st>>>(tv, tq, tql, p);
+        HS_LAUNCH_CHECK();
+        return HS_OK;
+    }
+    grid = grid / CL * CL;                      // whole clusters only (callers pick CL > 1 for n_tiles >= num_sms)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HS_CUDA(cudaLaunchKernelEx(&cfg, kern, tv, tq, tql, p));
     return HS_OK;
 }
 
-int dispatch_gemm(int kind, int mt, int epi, const CUtensorMap& tv, const CUtensorMap& tq, const CUtensorMap& tql,
+int dispatch_gemm(int kind, int mt, int epi, int cl, const CUtensorMap& tv, const CUtensorMap& tq, const CUtensorMap& tql,
                   const GemmParams& p, size_t smem, int num_sms, cudaStream_t st) {
-#define HS_GEMM_CASE(K, M, E) \
-    if (kind == K && mt == M && epi == E) return launch_gemm<K, M, E>(tv, tq, tql, p, smem, num_sms, st)
-    HS_GEMM_CASE(kKindBf16, 1, kEpiStore);
-    HS_GEMM_CASE(kKindBf16, 2, kEpiStore);
-    HS_GEMM_CASE(kKindBf16, 1, kEpiFilter);
-    HS_GEMM_CASE(kKindBf16, 2, kEpiFilter);
-    HS_GEMM_CASE(kKindTf32x3, 1, kEpiStore);
-    HS_GEMM_CASE(kKindTf32x3, 1, kEpiFilter);
+#define HS_GEMM_CASE(K, M, E, C) \
+    if (kind == K && mt == M && epi == E && cl == C) return launch_gemm<K, M, E, C>(tv, tq, tql, p, smem, num_sms, st)
+    HS_GEMM_CASE(kKindBf16, 1, kEpiStore, 1);
+    HS_GEMM_CASE(kKindBf16, 2, kEpiStore, 1);
+    HS_GEMM_CASE(kKindBf16, 1, kEpiFilter, 1);
+    HS_GEMM_CASE(kKindBf16, 2, kEpiFilter, 1);
+    HS_GEMM_CASE(kKindTf32x3, 1, kEpiStore, 1);
+    HS_GEMM_CASE(kKindTf32x3, 1, kEpiFilter, 1);
+    HS_GEMM_CASE(kKindBf16, 1, kEpiStore, 2);
+    HS_GEMM_CASE(kKindBf16, 2, kEpiStore, 2);
+    HS_GEMM_CASE(kKindBf16, 1, kEpiFilter, 2);
+    HS_GEMM_CASE(kKindBf16, 2, kEpiFilter, 2);
+    HS_GEMM_CASE(kKindBf16, 2, kEpiStore, 4);
+    HS_GEMM_CASE(kKindBf16, 2, kEpiFilter, 4);
+    HS_GEMM_CASE(kKindTf32x3, 1, kEpiStore, 2);
+    HS_GEMM_CASE(kKindTf32x3, 1, kEpiFilter, 2);
 #undef HS_GEMM_CASE
-    hs_set_error("dense_gemm: internal: no kernel for kind=%d mt=%d epi=%d", kind, mt, epi);
+    hs_set_error("dense_gemm: internal: no kernel for kind=%d mt=%d epi=%d cluster=%d", kind, mt, epi, cl);
     return HS_ERR_ARG;
+}
+
+// cluster size of the query-block multicast: only when the query operand streams (not resident) and the launch fills the
+// GPU; bf16 defaults to 2, tf32x3 (shared-memory bound, not L2 bound) to 1.  HS_GEMM_CLUSTER=1|2|4 overrides (A/B runs).
+int pick_cluster(int kind, int mt, const Plan& pl, int64_t n_tiles, int num_sms) {
+    static const int forced = [] {
+        const char* e = getenv("HS_GEMM_CLUSTER");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    if (pl.q_resident || n_tiles < 4 * (int64_t)num_sms || (num_sms % 4) != 0) return 1;
+    int cl = kind == kKindBf16 ? 2 : 1;
+    if (forced == 1 || forced == 2 || forced == 4) cl = forced;
+    if (cl == 4 && !(kind == kKindBf16 && mt == 2)) cl = 2;
+    return cl;
 }
 
 int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t d0, int64_t d1,
@@ -589,12 +701,13 @@ int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q,
             gemm_prepare_queries_kernel<kKindTf32x3><<<mt * kTileM, 32, 0, st>>>(queries, ld_q, idx->dim, b0, nq_valid,
                                                                                  (int)kpad, q_hi, (float*)q_lo, inv_qn);
         HS_LAUNCH_CHECK();
+        const int cl = pick_cluster(kind, mt, pl, (d1 - d0 + kTileN - 1) / kTileN, idx->num_sms);
         CUtensorMap tq, tql;
-        int rc = make_tmap(&tq, q_hi, mt * kTileM, kpad, elem);
+        int rc = make_tmap(&tq, q_hi, mt * kTileM, kpad, elem, kTileM / cl);      // box = the row slice one CTA fetches
         if (rc != HS_OK) return rc;
         tql = tq;
         if (kind == kKindTf32x3) {
-            rc = make_tmap(&tql, q_lo, mt * kTileM, kpad, elem);
+            rc = make_tmap(&tql, q_lo, mt * kTileM, kpad, elem, kTileM / cl);
             if (rc != HS_OK) return rc;
         }
         GemmParams p;
@@ -616,7 +729,7 @@ int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q,
         p.seg_cap = seg_cap;
         p.n_seg = hs_dense_gemm_filter_segments(idx, mode);
         p.doc_base = (uint32_t)idx->doc_base;
-        rc = dispatch_gemm(kind, mt, epi, tv, tq, tql, p, pl.smem, idx->num_sms, st);
+        rc = dispatch_gemm(kind, mt, epi, cl, tv, tq, tql, p, pl.smem, idx->num_sms, st);
         if (rc != HS_OK) return rc;
     }
     return HS_OK;

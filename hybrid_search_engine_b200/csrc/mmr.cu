@@ -175,8 +175,9 @@ __global__ void __launch_bounds__(kClThreads, 1) mmr_cluster_kernel(const MmrPar
     const int rank = (int)cluster.block_rank();
     const int b = blockIdx.x / kCluster;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // rows [rpc][ld] | rel [rpc] | ms [rpc] | vn [rpc] | alive [rpc]
-    float* rows = reinterpret_cast<float*>(mmr_smem);
+    // pick [ld] | rows [rpc][ld] | rel [rpc] | ms [rpc] | vn [rpc] | alive [rpc]
+    float* pick = reinterpret_cast<float*>(mmr_smem);             // local copy of the round's selected row
+    float* rows = pick + p.ld;
     double* rel = reinterpret_cast<double*>(rows + (size_t)rpc * p.ld);
     double* ms = rel + rpc;
     float* vn = reinterpret_cast<float*>(ms + rpc);
@@ -265,9 +266,16 @@ __global__ void __launch_bounds__(kClThreads, 1) mmr_cluster_kernel(const MmrPar
         if (it + 1 == p.k) break;
         // ---- the pick's row and norm come from its owner's shared memory (DSMEM); then score the local rows,
         //      kRowsAtOnce per warp so that the float64 chains and butterflies of different rows overlap
+        // DSMEM moves ~20 B/clk and the OWNER's shared-memory port pays for every reader, so each CTA fetches the row
+        // once (one float4 per thread) into its own shared memory and its 16 warps read the local copy
         const int owner = best / rpc, orow = best - owner * rpc;
-        const float* srow = cluster.map_shared_rank(rows, owner) + (size_t)orow * p.ld;
+        {
+            const float4* src = reinterpret_cast<const float4*>(cluster.map_shared_rank(rows, owner) + (size_t)orow * p.ld);
+            for (int e = tid; e < ld4; e += kClThreads) reinterpret_cast<float4*>(pick)[e] = src[e];
+        }
         const float sn = *(cluster.map_shared_rank(vn, owner) + orow);
+        __syncthreads();
+        const float* srow = pick;
         double q[kMaxChunks][4];
 #pragma unroll
         for (int c = 0; c < kMaxChunks; ++c) {
@@ -319,7 +327,7 @@ __global__ void __launch_bounds__(kClThreads, 1) mmr_cluster_kernel(const MmrPar
 }
 
 size_t mmr_cluster_smem(int rpc, int64_t ld) {
-    return (size_t)rpc * ld * sizeof(float) + (size_t)rpc * (2 * sizeof(double) + sizeof(float) + 1) + 64;
+    return (size_t)(rpc + 1) * ld * sizeof(float) + (size_t)rpc * (2 * sizeof(double) + sizeof(float) + 1) + 64;
 }
 
 }  // namespace

@@ -14,7 +14,7 @@ from typing import List, Sequence
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, devsort
 from ._lib import check, ptr, stream_ptr
 from .extractor import STOPWORDS, extract_tokens
 
@@ -91,24 +91,34 @@ class DeviceLexicalStats:
                 start = end
             h = torch.cat(hashes) if hashes else torch.zeros(0, dtype=torch.int64, device=dev)
             d = torch.cat(docs_of) if docs_of else torch.zeros(0, dtype=torch.int64, device=dev)
+            # token-level passes: the hand-written primitives of csrc/sort.cu (radix sort, binary search, run-length
+            # encoding, boundary counts, prefix sum)
             if self.remove_stopwords and h.numel():
-                keep = ~torch.isin(h, torch.from_numpy(STOP_HASHES).to(dev))
+                stop = torch.from_numpy(np.sort(STOP_HASHES)).to(dev)
+                at = devsort.lower_bound(stop, h).clamp_(max=stop.numel() - 1)
+                keep = stop[at] != h
                 h, d = h[keep], d[keep]
-            # ---- statistics (bm25.py:59-71): dl counts tokens after stop-word removal, duplicates included
-            dl = torch.bincount(d, minlength=n) if n else torch.zeros(0, dtype=torch.int64, device=dev)
+            # ---- statistics (bm25.py:59-71): dl counts tokens after stop-word removal, duplicates included.  Tokens
+            #      are in document order, so d << 32 is a sorted key column and dl is its per-"term" count
+            dl = devsort.term_doc_freqs(d << 32, n) if n else torch.zeros(0, dtype=torch.int64, device=dev)
             self.doc_lengths = dl.to(torch.int32)
             self.avg_doc_len = (int(dl.sum().item()) / n) if n > 0 else 0
-            uniq, inv = torch.unique(h, return_inverse=True) if h.numel() else (h, h)
+            if h.numel():
+                hs_sorted = devsort.sort_keys_(h.clone())                     # vocabulary = distinct hashes, ascending
+                uniq, _ = devsort.run_length_encode(hs_sorted)
+                del hs_sorted
+                inv = devsort.lower_bound(uniq, h)                            # term id of every token
+            else:
+                uniq, inv = h, h
             V = int(uniq.numel())
-            keys = (inv << 32) | d
-            keys, _ = torch.sort(keys)
-            uk, tf = torch.unique_consecutive(keys, return_counts=True) if keys.numel() else (keys, keys)
-            terms = uk >> 32
-            df = torch.bincount(terms, minlength=V) if V else torch.zeros(0, dtype=torch.int64, device=dev)
-            indptr = torch.zeros(V + 1, dtype=torch.int64, device=dev)
-            if V:
-                torch.cumsum(df, 0, out=indptr[1:])
-            self.indptr = indptr
+            keys = ((inv << 32) | d).contiguous()
+            if keys.numel():
+                devsort.sort_keys_(keys, devsort.byte_mask_for((0, max(n - 1, 1)), (32, max(V - 1, 1))))
+                uk, tf = devsort.run_length_encode(keys)
+            else:
+                uk, tf = keys, keys
+            df = devsort.term_doc_freqs(uk, V) if V else torch.zeros(0, dtype=torch.int64, device=dev)
+            self.indptr = devsort.exclusive_scan(df) if V else torch.zeros(1, dtype=torch.int64, device=dev)
             if uk.numel():
                 self.postings = torch.stack([(uk & 0xFFFFFFFF).to(torch.int32), tf.to(torch.int32)], dim=1)
             else:

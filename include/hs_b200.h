@@ -218,6 +218,23 @@ int hs_token_flags(const uint8_t* text, int64_t n_bytes, uint8_t* flags, void* s
 int hs_token_hashes(const uint8_t* text, int64_t n_bytes, const int64_t* starts, int64_t n_tokens, int64_t* hashes,
                     void* stream);
 
+/* ---- index-build primitives (BM25.fit's Counter / dict bookkeeping, bm25.py:56-71, as device passes over 64-bit
+ *      (term << 32 | doc) keys): stable LSD radix sort over the key bytes named in byte_mask (bit p = byte p; bytes
+ *      that are equal in every key may be left out; tmp: n keys of scratch), binary search in a sorted array, exclusive
+ *      prefix sum, run-length encoding of SORTED keys (uniq / start / counts sized n, start n + 1; *total = number
+ *      of runs, device scalar), and per-term posting counts df[t] from sorted unique keys (scratch: 2 * n_terms) */
+size_t hs_radix_sort_workspace_bytes(int64_t n);
+int hs_radix_sort_u64(uint64_t* keys, uint64_t* tmp, int64_t n, uint32_t byte_mask, void* workspace,
+                      size_t workspace_bytes, void* stream);
+size_t hs_scan_workspace_bytes(int64_t n);
+int hs_exclusive_scan_i64(const int64_t* in, int64_t* out, int64_t n, void* workspace, size_t workspace_bytes,
+                          void* stream);
+size_t hs_rle_workspace_bytes(int64_t n);
+int hs_run_length_encode_u64(const uint64_t* sorted_keys, int64_t n, uint64_t* uniq, int64_t* start, int32_t* counts,
+                             int64_t* total, void* workspace, size_t workspace_bytes, void* stream);
+int hs_lower_bound_i64(const int64_t* sorted, int64_t n, const int64_t* queries, int64_t m, int64_t* out, void* stream);
+int hs_term_doc_freqs(const uint64_t* uniq_keys, int64_t m, int64_t n_terms, int64_t* scratch, int64_t* df, void* stream);
+
 /* ---- synthetic corpus generators (counter-based; hybrid_search_engine_b200/synth.py is the spec) */
 int hs_synth_embeddings(float* out, int64_t row0, int64_t n, int32_t dim, int64_t ld, uint64_t seed_key,
                         void* stream);

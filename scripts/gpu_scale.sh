@@ -1,0 +1,20 @@
+# usage: bash scripts/gpu_scale.sh N [tag]   -- bench.py at N ranks: default hybrid workload (+ configs 3/4/5 when N == 8 or N == 1)
+N=$1; TAG=${2:-r2}
+mkdir -p gpurun_out
+run() {  # name, extra args
+  name=$1; shift
+  if [ "$N" = "1" ]; then
+    timeout -k 10 900 python bench.py --gpus 1 "$@" > gpurun_out/${TAG}_${name}_n1.json 2> gpurun_out/${TAG}_${name}_n1.err
+  else
+    timeout -k 10 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N "$@" > gpurun_out/${TAG}_${name}_n$N.json 2> gpurun_out/${TAG}_${name}_n$N.err
+  fi
+  echo "== $name n=$N rc=$?"; tail -c 600 gpurun_out/${TAG}_${name}_n$N.json; echo; tail -n 2 gpurun_out/${TAG}_${name}_n$N.err | cut -c1-300
+}
+run hybrid --steps 20 --warmup 5
+if [ "$N" = "8" ] || [ "$N" = "1" ]; then
+  run hybrid_b8 --steps 20 --warmup 5 --batch 8 --dense-mode fp32 --no-extras --no-cpu-baseline
+  run bm25 --workload bm25 --steps 10 --warmup 3
+  run multi_stage --workload multi_stage --steps 5 --warmup 3
+  run diversity --workload diversity --steps 3 --warmup 3 --batch 4096
+fi

@@ -147,3 +147,35 @@ def test_bm25plus_score_and_search_on_device(hs):
             ids = orc.canonical_topk(ref, 25)
             assert [i for i, _ in top] == ids.tolist(), (name, q)
             assert [s for _, s in top] == [float(ref[i]) for i in ids], (name, q)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 2047, 2048, 2049, 70_001, 3_000_000])
+def test_device_sort_primitives_match_library_results(hs, n):
+    """csrc/sort.cu (radix sort, run-length encoding, per-term counts, prefix sum, binary search) vs torch's library
+    sort / unique_consecutive / bincount / cumsum / searchsorted on the same keys."""
+    from hybrid_search_engine_b200 import devsort
+    g = torch.Generator(device="cuda").manual_seed(n)
+    V, D = 5000, 1 << 20
+    terms = torch.randint(0, V, (n,), generator=g, device="cuda", dtype=torch.int64)
+    terms = torch.minimum(terms, torch.randint(0, V, (n,), generator=g, device="cuda", dtype=torch.int64))   # skewed
+    docs = torch.randint(0, min(D, max(n // 3, 1)), (n,), generator=g, device="cuda", dtype=torch.int64)
+    keys = (terms << 32) | docs
+    want = torch.sort(keys).values
+    got = devsort.sort_keys_(keys.clone(), devsort.byte_mask_for((0, D - 1), (32, V - 1)))
+    assert torch.equal(got, want)
+    assert torch.equal(devsort.sort_keys_(keys.clone()), want)                       # all eight passes
+    full = torch.randint(0, 2 ** 62, (n,), generator=g, device="cuda", dtype=torch.int64)
+    assert torch.equal(devsort.sort_keys_(full.clone()), torch.sort(full).values)    # every byte varies
+    uk, tf = devsort.run_length_encode(want)
+    uk_w, tf_w = torch.unique_consecutive(want, return_counts=True)
+    assert torch.equal(uk, uk_w) and torch.equal(tf.to(torch.int64), tf_w)
+    df = devsort.term_doc_freqs(uk, V)
+    assert torch.equal(df, torch.bincount(uk >> 32, minlength=V))
+    assert torch.equal(devsort.term_doc_freqs(want, V), torch.bincount(want >> 32, minlength=V))   # duplicates allowed
+    scan = devsort.exclusive_scan(df)
+    assert scan.numel() == V + 1 and int(scan[0]) == 0 and torch.equal(scan[1:], torch.cumsum(df, 0))
+    big = torch.randint(0, 1000, (n,), generator=g, device="cuda", dtype=torch.int64)
+    sb = devsort.exclusive_scan(big)
+    assert torch.equal(sb[1:], torch.cumsum(big, 0))
+    q = torch.randint(0, int(uk_w.max()) + 5, (min(n, 1000),), generator=g, device="cuda", dtype=torch.int64)
+    assert torch.equal(devsort.lower_bound(uk, q), torch.searchsorted(uk_w, q))
