@@ -687,7 +687,8 @@ def run_ours(args):
     roof.update({"peak_source": peak_src, "traffic": None, "kernels": kernels})
     try:    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, when one matches
         ent = json.load(open(os.path.join(ROOT, "profiles", "dense_traffic.json")))["entries"]
-        roof["traffic"] = ent.get(f"{args.dense_mode}_n{n_shard}_ld{shard.ld}_q{sub}") or ent.get(f"n{n_shard}_ld{shard.ld}_q{min(sub, 8)}")
+        roof["traffic"] = ent.get(f"{args.dense_mode}_n{n_shard}_ld{shard.ld}_q{sub}") if tensor_mode else \
+            ent.get(f"n{n_shard}_ld{shard.ld}_q{min(sub, 8)}")
     except Exception:
         pass
 
@@ -720,16 +721,21 @@ def run_ours(args):
     # ---------------------------------------------------------------- extra points of the north star (N = 1, hybrid)
     if wl == "hybrid" and world == 1 and not args.no_extras:
         pts = []
-        for pb, mode in ((1, "fp32"), (8, "fp32")):
-            e2 = SearchEngine(shard, max_batch=pb, dense_mode=mode)
+        # SURVEY 8(d) north-star points B in {1, 32, 256} (+ 8, the largest batch of ONE pass of the CUDA-core fp32 scan)
+        for pb, mode in ((1, "fp32"), (8, "fp32"), (32, "tf32x3"), (256, "tf32x3")):
+            if pb == B and mode == args.dense_mode:
+                continue
+            e2 = SearchEngine(shard, max_batch=min(pb, 128), dense_mode=mode)
             st_ = []
             for s in range(8):
                 qb = batch_of(s, pb)
                 qd = e2.upload_vectors(qb.vectors).clone()
                 qt, qi, qo = [x.clone() for x in e2.upload_terms(qb.term_ids)]
-                st_.append((qd, qt, qi, qo, e2._n_tokens))
+                st_.append((qd, qt, qi, qo, e2._n_tokens, qb))
 
             def small_step(x, tm=None):
+                if pb > 128:                    # two corpus passes of 128: the engine's own sub-batch loop
+                    return e2.search_hybrid_bm25(x[5], k, 0.6, 0.4)
                 stats = e2._stats(pb)
                 if tm is not None:
                     a, b_ = ev(), ev()
@@ -751,9 +757,14 @@ def run_ours(args):
             b_.record()
             torch.cuda.synchronize()
             ms = a.elapsed_time(b_) / 16
-            dms = float(np.mean([x.elapsed_time(y) for x, y in tm])) / e2.dense_launches(pb)
-            pts.append({"queries_per_step": pb, "dense_mode": mode, "value": pb / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
-                        "dense_scan_frac_hbm": n_shard * shard.ld * 4 / dms / 1e6 / hbm_peak, "dense_scan_launch_ms": dms})
+            pt = {"queries_per_step": pb, "dense_mode": mode, "value": pb / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
+                  "note": "device-resident inputs" if pb <= 128 else "through SearchEngine.search_hybrid_bm25 (host inputs)"}
+            if tm:
+                dms = float(np.mean([x.elapsed_time(y) for x, y in tm])) / e2.dense_launches(pb)
+                pt.update({"dense_launch_ms": dms, "dense_frac_hbm": n_shard * shard.ld * 4 / dms / 1e6 / hbm_peak})
+                if mode == "tf32x3":
+                    pt["dense_frac_tensor"] = 6.0 * pb * n_shard * shard.ld / dms / 1e9 / (bf16_peak / 2)
+            pts.append(pt)
             del e2
         line["points"] = pts
     if world == 1 and not args.no_cpu_baseline and wl == "hybrid":

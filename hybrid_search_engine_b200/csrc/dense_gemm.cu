@@ -420,22 +420,27 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                         }
                     }
                     const int nvalid = ndoc - c0 < 32 ? ndoc - c0 : 32;    // columns of this chunk that are real docs
-                    if (active[mt]) {
-                        if (nvalid == 32) {
+                    // chunk extrema first (a tree of 3-input min / max, no per-element predicates on a full chunk): they
+                    // feed the query's running min / max, and the FILTER epilogue tests ONE value against the threshold
+                    float cmn = __int_as_float(0x7f800000), cmx = __int_as_float(0xff800000);
+                    if (nvalid == 32) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                mn[mt] = fminf(mn[mt], v[j]);
-                                mx[mt] = fmaxf(mx[mt], v[j]);
-                            }
-                        } else {
+                        for (int j = 0; j < 32; ++j) {
+                            cmn = fminf(cmn, v[j]);
+                            cmx = fmaxf(cmx, v[j]);
+                        }
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (j < nvalid) {
-                                    mn[mt] = fminf(mn[mt], v[j]);
-                                    mx[mt] = fmaxf(mx[mt], v[j]);
-                                }
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < nvalid) {
+                                cmn = fminf(cmn, v[j]);
+                                cmx = fmaxf(cmx, v[j]);
                             }
                         }
+                    }
+                    if (active[mt]) {
+                        mn[mt] = fminf(mn[mt], cmn);
+                        mx[mt] = fmaxf(mx[mt], cmx);
                     }
                     if constexpr (EPI == kEpiStore) {
                         // transpose through smem so that the global stores run along the docs of ONE query (128 contiguous
@@ -451,16 +456,13 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                         }
                         __syncwarp();
                     } else {
-                        if (active[mt]) {
-                            unsigned hit = 0;                      // columns at or above the query's starting bound
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) hit |= (v[j] >= thr[mt] && j < nvalid) ? (1u << j) : 0u;
-                            if (hit != 0) {                        // rare
-                                unsigned long long* seg = p.cand + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
-                                                                    (blockIdx.x * kEpiGroups + grp)) * p.seg_cap;
+                        if (active[mt] && cmx >= thr[mt]) {        // rare: some column reaches the query's starting bound
+                            unsigned long long* seg = p.cand + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
+                                                                (blockIdx.x * kEpiGroups + grp)) * p.seg_cap;
+                            {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
-                                    if ((hit >> j) & 1u) {
+                                    if (j < nvalid && v[j] >= thr[mt]) {
                                         if (n_app[mt] < (uint32_t)p.seg_cap)
                                             seg[n_app[mt]] = hs_make_key(v[j], p.doc_base + (uint32_t)(doc0 + c0 + j));
                                         ++n_app[mt];

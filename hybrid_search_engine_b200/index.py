@@ -103,6 +103,7 @@ class DeviceIndex:
         for s in range(0, self.n_docs, step):                   # chunked: no second float32 copy
             v16[s:s + step, :self.dim] = self.vectors[s:s + step, :self.dim].to(torch.bfloat16)
         self.vectors_bf16 = v16
+        self.ld_bf16 = ld16
         check(self.lib.hs_index_set_dense_bf16(self.handle, ptr(v16), ld16), "hs_index_set_dense_bf16")
 
     # ------------------------------------------------------------------ lexical part

@@ -231,11 +231,13 @@ class HybridBM25Pipeline(BasePipeline):
             sc, ids = s_dev.cpu().numpy(), i_dev.cpu().numpy()
         meta = {"pipeline": "hybrid_bm25", "semantic_weight": self.semantic_weight,
                 "bm25_weight": self.bm25_weight}
+        docs = self.documents
         for qi, q in enumerate(queries):
+            # iterating a float32 array yields np.float32 scalars (the reference's score type, pipelines.py:347); ids as ints
             out.append(PipelineResult(
                 query=q,
-                results=[{"score": np.float32(s), "content": self.documents[int(d)], "doc_id": int(d)}
-                         for s, d in zip(sc[qi], ids[qi]) if d >= 0],
+                results=[{"score": s, "content": docs[d], "doc_id": d}
+                         for s, d in zip(list(sc[qi]), ids[qi].tolist()) if d >= 0],
                 metadata=dict(meta), highlighted=None))
         return out
 
