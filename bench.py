@@ -23,7 +23,10 @@ is FIXED as N grows (doc-sharded) => "scaling": "strong".
              dictionaries are inside the timed region
 * ``roofline``  the dominant kernel of the step + ``kernels[]`` for dense / bm25 / select and the whole
              step against SURVEY.md section 8(d)'s algorithmic bytes (tensor modes: executed MMA flops
-             against the measured bf16 peak, halved for TF32)
+             against the measured bf16 peak, halved for TF32).  The default dense mode ``bf16_exact`` screens
+             with the bf16 tcgen05 GEMM and verifies in the conformance order: its results are the ``exact``
+             mode's bit for bit (``parity.verify_flagged_queries_in_timed_steps`` counts queries whose proof
+             failed and that the serving API would redo exactly; the device-timed step does not redo them)
 * ``parity``  top-k ids of the last batch vs the float64-accumulated ``exact`` mode, and the sha256 of the
              exact-mode top-100 (ids + scores) of a FIXED 64-query batch compared with the constant committed
              in tests/golden/bench_digests.json (generated at N = 1): sharded == unsharded, bit for bit
@@ -49,7 +52,7 @@ UNIT = "queries/s"
 WORKLOADS = {
     # name: (metric, defaults)
     "hybrid": ("hybrid_bm25 queries/sec @10M docs 384-d top-100",
-               dict(n_docs=10_000_000, dim=384, batch=128, top_k=100, dense_mode="tf32x3")),
+               dict(n_docs=10_000_000, dim=384, batch=128, top_k=100, dense_mode="bf16_exact")),
     "bm25": ("bm25 queries/sec @50M docs top-100 (BASELINE config 3)",
              dict(n_docs=50_000_000, dim=384, batch=32, top_k=100, dense_mode="fp32")),
     "multi_stage": ("multi_stage stages 1-2 queries/sec @10M docs 768-d bf16, dense top-100 -> BM25 top-20 (BASELINE config 4)",
@@ -71,7 +74,7 @@ def parse_args():
     ap.add_argument("--dim", type=int, default=None)
     ap.add_argument("--batch", type=int, default=None, help="queries per step")
     ap.add_argument("--top-k", type=int, default=None)
-    ap.add_argument("--dense-mode", default=None, choices=["exact", "fp32", "tf32x3", "bf16"])
+    ap.add_argument("--dense-mode", default=None, choices=["exact", "fp32", "tf32x3", "bf16", "bf16_exact"])
     ap.add_argument("--cpu-sample-docs", type=int, default=500_000)
     ap.add_argument("--ref-docs", type=int, default=50_000, help="docs of the unmodified-reference CPU runs")
     ap.add_argument("--ref-workers", type=int, default=0, help="--impl reference: worker processes (0 = all cores, <= 32)")
@@ -378,14 +381,15 @@ def run_ours(args):
     t0 = time.perf_counter()
     shard = synth_device.build_synthetic_shard(spec, lo, hi, device, group=group, dense=wl != "bm25",
                                                lexical=wl != "diversity")
-    if args.dense_mode == "bf16" and wl != "bm25":
+    if args.dense_mode in ("bf16", "bf16_exact") and wl != "bm25":
         shard.ensure_bf16()
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t0
 
     B, k = args.batch, args.top_k
-    tensor_mode = args.dense_mode in ("tf32x3", "bf16")
-    sub = min(B, 128 if args.dense_mode == "tf32x3" else (256 if args.dense_mode == "bf16" else 8))
+    tensor_mode = args.dense_mode in ("tf32x3", "bf16", "bf16_exact")
+    sub = min(B, 128 if args.dense_mode == "tf32x3" else (256 if args.dense_mode in ("bf16", "bf16_exact") else 8))
+    vflags = torch.zeros(max(B, 1), dtype=torch.int32, device=device)      # bf16_exact: queries the verification flagged
     if wl == "bm25":
         sub = min(B, 32)
     eng = SearchEngine(shard, group=group, max_batch=sub, dense_mode=args.dense_mode)
@@ -421,6 +425,17 @@ def run_ours(args):
         for bi, s in enumerate(range(0, B, sub)):
             nb = min(B, s + sub) - s
             stats = eng._stats(nb)
+            if args.dense_mode == "bf16_exact":      # screen (bf16 GEMM) + exact verification: one fused chain
+                qt, qi, qo, n_tok = terms[bi]
+                eng.phase_events = [] if timers is not None else None
+                keys = eng._verified_sub_batch(qd[s:s + nb], nb, stats,
+                                               lambda st_: eng.bm25_score(qt, qi, qo, nb, st_, n_tok), 2, 0.6, 0.4, k,
+                                               vflags[s:s + nb], _lib.VERIFY_EPS["bf16_exact"])
+                out = eng.unpack(keys)
+                if timers is not None:               # [start, after GEMM, after BM25, after verify + select + merge]
+                    timers.append(eng.phase_events)
+                    eng.phase_events = None
+                continue
             if timers is not None:
                 e = [ev() for _ in range(4)]
                 e[0].record()
@@ -625,24 +640,27 @@ def run_ours(args):
     # ---------------------------------------------------------------- rooflines (rank 0; per-shard figures)
     kernels = []
     passes = eng.dense_launches(sub) * ((B + sub - 1) // sub) if wl in ("hybrid",) else 0
+    split = True
     if wl == "hybrid":
         elem = 4
-        if args.dense_mode == "bf16":
+        if args.dense_mode in ("bf16", "bf16_exact"):
             elem = 2
         dense_bytes = n_shard * shard.ld * elem * passes + (B * n_shard * 4 if tensor_mode else 0)
-        ent = {"name": "dense_gemm_kernel (tcgen05 %s)" % args.dense_mode if tensor_mode else "dense_scan_kernel",
+        gname = {"bf16_exact": "bf16 STORE + extreme lists"}.get(args.dense_mode, args.dense_mode)
+        ent = {"name": "dense_gemm_kernel (tcgen05 %s)" % gname if tensor_mode else "dense_scan_kernel",
                "ms_per_step": dense_ms, "launches_per_step": passes, "alg_bytes_per_step": dense_bytes,
                "hbm_GBps": dense_bytes / dense_ms / 1e6, "frac_hbm": dense_bytes / dense_ms / 1e6 / hbm_peak}
         if tensor_mode:
             mul = 3 if args.dense_mode == "tf32x3" else 1
             peak_t = bf16_peak / (2 if args.dense_mode == "tf32x3" else 1)
+            ent["note"] = "bf16 MMA against the measured sustained bf16 peak; the kernel is HBM-bound at <= 256 queries per pass"
             fl = 2.0 * B * n_shard * shard.ld * mul
             ent.update({"mma_tflops": fl / dense_ms / 1e9, "tensor_peak_tflops": peak_t, "frac_tensor": fl / dense_ms / 1e9 / peak_t,
                         "algorithmic_tflops": 2.0 * B * n_shard * args.dim / dense_ms / 1e9,
                         "note": "tf32x3 issues 3 TF32 MMAs per K step (hi*hi + lo*hi + hi*lo); peak = measured bf16 sustained / 2"
                         if mul == 3 else "bf16 MMA against the measured sustained bf16 peak"})
         kernels.append(ent)
-    if wl in ("hybrid", "bm25"):
+    if (wl == "hybrid" and split) or wl == "bm25":
         # bytes_bm25(query) = 8 * P(q) + 8 * N_shard, P from the GLOBAL df scaled to the shard
         P = 0.0
         for s in range(args.warmup, args.warmup + args.steps):
@@ -653,10 +671,13 @@ def run_ours(args):
         kernels.append({"name": "bm25_ranges_kernel + bm25_batch_kernel", "ms_per_step": bm25_ms, "alg_bytes_per_step": bm_bytes,
                         "postings_per_step": P, "hbm_GBps": bm_bytes / bm25_ms / 1e6, "frac_hbm": bm_bytes / bm25_ms / 1e6 / hbm_peak})
         sel_bytes = (8 if wl == "hybrid" else 4) * n_shard * B
-        kernels.append({"name": "fuse_blockmax + fuse_bound + fuse_topk + topk_merge + keys_unpack" + (" (+ C2/C1 exchange)" if world > 1 else ""),
+        sname = "fuse_blockmax + fuse_bound + fuse_topk + topk_merge + keys_unpack"
+        if args.dense_mode == "bf16_exact" and wl == "hybrid":
+            sname = "verify_stats + fuse_blockmax + fuse_bound + fuse_topk (k' = 512) + topk_merge + verify_topk + keys_unpack"
+        kernels.append({"name": sname + (" (+ C2/C1 exchange)" if world > 1 else ""),
                         "ms_per_step": select_ms, "alg_bytes_per_step": sel_bytes, "hbm_GBps": sel_bytes / select_ms / 1e6,
                         "frac_hbm": sel_bytes / select_ms / 1e6 / hbm_peak})
-    if wl == "hybrid":
+    if wl == "hybrid" and split:
         # bytes_hybrid(B) = N d 4 + B (8 P + 8 N) + B 8 N   (one corpus pass whatever B)
         step_bytes = n_shard * shard.ld * 4 + kernels[1]["alg_bytes_per_step"] + 8 * n_shard * B
         step_ent = {"name": "step (bytes_hybrid of SURVEY 8(d))", "ms_per_step": step_ms, "alg_bytes_per_step": step_bytes,
@@ -671,6 +692,8 @@ def run_ours(args):
         roof.update({"launch_ms": dom["ms_per_step"] / max(dom.get("launches_per_step", 1), 1),
                      "share_of_step": dom["ms_per_step"] / step_ms})
         kernels.append(step_ent)
+    elif wl == "hybrid":
+        pass
     elif wl == "bm25":
         dom = kernels[0]
         roof = {"bound": "hbm", "kernel": dom["name"], "achieved": dom["hbm_GBps"], "peak": hbm_peak, "unit": "GB/s",
@@ -693,7 +716,10 @@ def run_ours(args):
         pass
 
     dtype = {"fp32": "f32", "exact": "f32 (f64-accumulated dot, f64 BM25)", "tf32x3": "f32 (3xTF32 tensor-core dot, f64 BM25)",
-             "bf16": "bf16 (dense) + f64 BM25"}[args.dense_mode]
+             "bf16": "bf16 (dense) + f64 BM25",
+             "bf16_exact": "bf16 screen + f64-accumulated exact verification (results of the exact mode), f64 BM25"}[args.dense_mode]
+    if args.dense_mode == "bf16_exact":
+        parity["verify_flagged_queries_in_timed_steps"] = int((vflags != 0).sum().item())
     workload = {
         "hybrid": f"hybrid_bm25 (0.6/0.4, k1=1.5, b=0.75) top-{k} over {args.n_docs} Zipfian docs x {args.dim}-d fp32, vocab {args.vocab}, avg 200 tokens/doc",
         "bm25": f"bm25 top-{k} over a {args.n_docs}-doc Zipfian inverted index (avg 200 terms/doc, vocab {args.vocab})",
@@ -722,10 +748,10 @@ def run_ours(args):
     if wl == "hybrid" and world == 1 and not args.no_extras:
         pts = []
         # SURVEY 8(d) north-star points B in {1, 32, 256} (+ 8, the largest batch of ONE pass of the CUDA-core fp32 scan)
-        for pb, mode in ((1, "fp32"), (8, "fp32"), (32, "tf32x3"), (256, "tf32x3")):
+        for pb, mode in ((1, "fp32"), (8, "fp32"), (32, "bf16_exact"), (128, "tf32x3"), (256, "bf16_exact")):
             if pb == B and mode == args.dense_mode:
                 continue
-            e2 = SearchEngine(shard, max_batch=min(pb, 128), dense_mode=mode)
+            e2 = SearchEngine(shard, max_batch=min(pb, 128 if mode == "tf32x3" else 256), dense_mode=mode)
             st_ = []
             for s in range(8):
                 qb = batch_of(s, pb)
@@ -734,7 +760,7 @@ def run_ours(args):
                 st_.append((qd, qt, qi, qo, e2._n_tokens, qb))
 
             def small_step(x, tm=None):
-                if pb > 128:                    # two corpus passes of 128: the engine's own sub-batch loop
+                if mode == "bf16_exact":        # the verified chain through the engine call (host inputs)
                     return e2.search_hybrid_bm25(x[5], k, 0.6, 0.4)
                 stats = e2._stats(pb)
                 if tm is not None:
@@ -758,7 +784,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             ms = a.elapsed_time(b_) / 16
             pt = {"queries_per_step": pb, "dense_mode": mode, "value": pb / ms * 1e3, "unit": UNIT, "ms_per_step": ms,
-                  "note": "device-resident inputs" if pb <= 128 else "through SearchEngine.search_hybrid_bm25 (host inputs)"}
+                  "note": "device-resident inputs" if mode != "bf16_exact" else "through SearchEngine.search_hybrid_bm25 (host inputs)"}
             if tm:
                 dms = float(np.mean([x.elapsed_time(y) for x, y in tm])) / e2.dense_launches(pb)
                 pt.update({"dense_launch_ms": dms, "dense_frac_hbm": n_shard * shard.ld * 4 / dms / 1e6 / hbm_peak})

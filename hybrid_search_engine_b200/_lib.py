@@ -16,7 +16,13 @@ LIB_PATH = os.path.join(_HERE, "libhs_b200.so")
 HS_DENSE_EXACT, HS_DENSE_FP32, HS_DENSE_BF16, HS_DENSE_TF32X3 = 0, 1, 2, 3
 HS_FUSE_RAW, HS_FUSE_SEARCHER, HS_FUSE_HYBRID_BM25 = 0, 1, 2
 HS_TOPK_MAX = 2048
-DENSE_MODES = {"exact": HS_DENSE_EXACT, "fp32": HS_DENSE_FP32, "bf16": HS_DENSE_BF16, "tf32x3": HS_DENSE_TF32X3}
+# "bf16_exact": screen with the bf16 tensor-core GEMM, verify in the conformance order -> the exact mode's results
+DENSE_MODES = {"exact": HS_DENSE_EXACT, "fp32": HS_DENSE_FP32, "bf16": HS_DENSE_BF16, "tf32x3": HS_DENSE_TF32X3,
+               "bf16_exact": HS_DENSE_BF16}
+# bound on |score - exact cosine| of a tensor-core mode: bf16 operands carry a relative rounding error <= 2^-9 each, so
+# |sum q~v~ - sum qv| <= (2^-8 + 2^-18) sum|q_i v_i| <= 2^-8 |q||v| (Cauchy-Schwarz); + 2^-13 for the tensor core's
+# truncating float32 accumulation (measured 2^-20) and the float32 scaling by the norms
+VERIFY_EPS = {"bf16_exact": 2.0 ** -8 * 1.001 + 2.0 ** -13 + 2.0 ** -20}
 
 _vp, _i32, _i64, _u32, _u64, _f64, _sz = (C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64,
                                           C.c_double, C.c_size_t)
@@ -47,6 +53,9 @@ SIGNATURES = {
     "hs_topk_select": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _sz, _vp, _vp]),
     "hs_keys_kth_score": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "hs_dense_gemm_filter_segments": (_i32, [_vp, _i32]),
+    "hs_dense_gemm_ext": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i64, _vp, _sz, _vp, _i64, _vp, _vp, _vp, _i32, _f64, _vp]),
+    "hs_verify_stats": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp]),
+    "hs_verify_topk": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _f64, _f64, _vp, _i32, _i32, _f64, _vp, _vp, _vp]),
     "hs_cand_select": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _f64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hs_bm25_workspace_bytes": (_sz, [_i64, _i32]),
     "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),

@@ -141,6 +141,41 @@ static inline cudaError_t hs_smem_limit(Kern kern, size_t smem, size_t (&cache)[
     return e;
 }
 
+// cosine of query q (float32 [dim], |q| = qn) and row v (|v| = vn) in the CONFORMANCE order, one warp per pair:
+// element e = 128 c + 4 lane + j accumulated in float64 over (c, j), lanes combined 16, 8, 4, 2, 1, then the
+// reference's float32 steps f32(dot) / (f32|q| * f32|v|) with its zero-norm rules (utils.py:44-52).  Bit-identical to
+// dense_scan_kernel<EXACT> and to oracle/hybrid_oracle.py:cosine_exact.  All lanes return the value.
+__device__ __forceinline__ float hs_exact_cos_warp(const float* __restrict__ q, float qn, const float* __restrict__ v,
+                                                   float vn, int dim, int64_t ld, int lane) {
+    double acc = 0.0;
+    const int nchunk = (dim + 127) / 128;
+    for (int c = 0; c < nchunk; ++c) {
+        const int e = c * 128 + lane * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < ld) x = *reinterpret_cast<const float4*>(v + e);
+        const float q0 = e + 0 < dim ? q[e + 0] : 0.f, q1 = e + 1 < dim ? q[e + 1] : 0.f;
+        const float q2 = e + 2 < dim ? q[e + 2] : 0.f, q3 = e + 3 < dim ? q[e + 3] : 0.f;
+        acc = __fma_rn((double)x.x, (double)q0, acc);
+        acc = __fma_rn((double)x.y, (double)q1, acc);
+        acc = __fma_rn((double)x.z, (double)q2, acc);
+        acc = __fma_rn((double)x.w, (double)q3, acc);
+    }
+    const float dot = __double2float_rn(hs_warp_sum_f64(acc));
+    return (qn != 0.0f && vn != 0.0f) ? __fdiv_rn(dot, __fmul_rn(qn, vn)) : 0.0f;
+}
+// f32(sqrt(sum64 q^2)) in the same order (dense_scan_kernel's query norm); all lanes return the value
+__device__ __forceinline__ float hs_exact_norm_warp(const float* __restrict__ q, int dim, int lane) {
+    double qq = 0.0;
+    const int nchunk = (dim + 127) / 128;
+    for (int c = 0; c < nchunk; ++c)
+        for (int j = 0; j < 4; ++j) {
+            const int e = c * 128 + lane * 4 + j;
+            const float x = e < dim ? q[e] : 0.f;
+            qq = __fma_rn((double)x, (double)x, qq);
+        }
+    return __double2float_rn(__dsqrt_rn(hs_warp_sum_f64(qq)));
+}
+
 static inline int hs_num_sms(int device) {
     int n = 148;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);

@@ -170,6 +170,13 @@ struct GemmParams {
     unsigned long long* cand;    // [B, n_seg, seg_cap] ranking keys
     unsigned int* cand_cnt;      // [B, n_seg] keys the segment's owner wanted to append (> seg_cap = overflow)
     int seg_cap, n_seg;
+    // STORE epilogue, optional (exact verification of an approximate scan, hs_verify_*): every score within eps2 of the
+    // thread's running max (min) is appended to the hi (lo) side of the (query, segment) list -- a superset of the docs
+    // whose EXACT cosine can be the query's global max (min) when |score - exact| <= eps2 / 2
+    unsigned long long* ext;     // [B, n_seg, 2, ext_cap] keys (score, shard-local doc)
+    unsigned int* ext_cnt;       // [B, n_seg, 2]
+    int ext_cap;
+    float eps2;
     uint32_t doc_base;           // global id of shard-local doc 0
 };
 
@@ -360,6 +367,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
         const int etid = e * 32 + lane;                           // 0..127 within the epilogue group
         float inv_qn[MT], mn[MT], mx[MT], thr[MT];
         uint32_t n_app[MT];                                       // FILTER: keys appended to this thread's segments
+        uint32_t n_hi[MT], n_lo[MT];                              // STORE + ext: entries of the extreme-candidate lists
         bool active[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -369,6 +377,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             mn[mt] = __int_as_float(0x7f800000);
             mx[mt] = __int_as_float(0xff800000);
             n_app[mt] = 0;
+            n_hi[mt] = n_lo[mt] = 0;
             thr[mt] = (EPI == kEpiFilter && active[mt] && p.thr != nullptr) ? __ldg(p.thr + p.b0 + b)
                                                                              : __int_as_float(0xff800000);
         }
@@ -443,6 +452,30 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                         mx[mt] = fmaxf(mx[mt], cmx);
                     }
                     if constexpr (EPI == kEpiStore) {
+                        if (p.ext != nullptr && active[mt]) {      // warp-uniform on p.ext; both tests are rare after the first tiles
+                            unsigned long long* lst = p.ext + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
+                                                               (blockIdx.x * kEpiGroups + grp)) * 2 * p.ext_cap;
+                            if (cmx >= mx[mt] - p.eps2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if (j < nvalid && v[j] >= mx[mt] - p.eps2) {
+                                        if (n_hi[mt] < (uint32_t)p.ext_cap)
+                                            lst[n_hi[mt]] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
+                                        ++n_hi[mt];
+                                    }
+                                }
+                            }
+                            if (cmn <= mn[mt] + p.eps2) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    if (j < nvalid && v[j] <= mn[mt] + p.eps2) {
+                                        if (n_lo[mt] < (uint32_t)p.ext_cap)
+                                            lst[p.ext_cap + n_lo[mt]] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
+                                        ++n_lo[mt];
+                                    }
+                                }
+                            }
+                        }
                         // transpose through smem so that the global stores run along the docs of ONE query (128 contiguous
                         // bytes per instruction)
 #pragma unroll
@@ -482,6 +515,14 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             for (int mt = 0; mt < MT; ++mt)
                 if (active[mt])
                     p.cand_cnt[(int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg + (blockIdx.x * kEpiGroups + grp)] = n_app[mt];
+        } else if (p.ext != nullptr) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                if (active[mt]) {
+                    unsigned int* c = p.ext_cnt + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg + (blockIdx.x * kEpiGroups + grp)) * 2;
+                    c[0] = n_hi[mt];
+                    c[1] = n_lo[mt];
+                }
         }
         if (p.stats != nullptr) {
 #pragma unroll
@@ -640,8 +681,6 @@ int dispatch_gemm(int kind, int mt, int epi, int cl, const CUtensorMap& tv, cons
     HS_GEMM_CASE(kKindBf16, 2, kEpiStore, 2);
     HS_GEMM_CASE(kKindBf16, 1, kEpiFilter, 2);
     HS_GEMM_CASE(kKindBf16, 2, kEpiFilter, 2);
-    HS_GEMM_CASE(kKindBf16, 2, kEpiStore, 4);
-    HS_GEMM_CASE(kKindBf16, 2, kEpiFilter, 4);
     HS_GEMM_CASE(kKindTf32x3, 1, kEpiStore, 2);
     HS_GEMM_CASE(kKindTf32x3, 1, kEpiFilter, 2);
 #undef HS_GEMM_CASE
@@ -650,7 +689,7 @@ int dispatch_gemm(int kind, int mt, int epi, int cl, const CUtensorMap& tv, cons
 }
 
 // cluster size of the query-block multicast: only when the query operand streams (not resident) and the launch fills the
-// GPU; bf16 defaults to 2, tf32x3 (shared-memory bound, not L2 bound) to 1.  HS_GEMM_CLUSTER=1|2|4 overrides (A/B runs).
+// GPU; bf16 defaults to 2, tf32x3 (shared-memory bound, not L2 bound) to 1.  HS_GEMM_CLUSTER=1|2 overrides (A/B runs).
 int pick_cluster(int kind, int mt, const Plan& pl, int64_t n_tiles, int num_sms) {
     static const int forced = [] {
         const char* e = getenv("HS_GEMM_CLUSTER");
@@ -658,14 +697,14 @@ int pick_cluster(int kind, int mt, const Plan& pl, int64_t n_tiles, int num_sms)
     }();
     if (pl.q_resident || n_tiles < 4 * (int64_t)num_sms || (num_sms % 4) != 0) return 1;
     int cl = kind == kKindBf16 ? 2 : 1;
-    if (forced == 1 || forced == 2 || forced == 4) cl = forced;
-    if (cl == 4 && !(kind == kKindBf16 && mt == 2)) cl = 2;
+    if (forced == 1 || forced == 2) cl = forced;      // 4 was measured and dropped: it strands 16 of the 148 SMs (1.8x slower)
     return cl;
 }
 
 int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t d0, int64_t d1,
              void* workspace, size_t workspace_bytes, int epi, float* cos, int64_t cos_ld, const float* thr,
-             uint64_t* cand, int32_t seg_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream, const char* who) {
+             uint64_t* cand, int32_t seg_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream, const char* who,
+             uint64_t* ext = nullptr, uint32_t* ext_cnt = nullptr, int32_t ext_cap = 0, float eps2 = 0.f) {
     HS_REQUIRE(idx != nullptr, "%s: idx is null", who);
     HS_REQUIRE(mode == HS_DENSE_BF16 || mode == HS_DENSE_TF32X3, "%s: mode %d is not a tensor-core mode", who, mode);
     HS_REQUIRE(d0 >= 0 && d0 <= d1 && d1 <= idx->n_docs, "%s: doc range [%lld, %lld) outside the shard", who,
@@ -730,6 +769,10 @@ int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q,
         p.cand_cnt = cand_cnt;
         p.seg_cap = seg_cap;
         p.n_seg = hs_dense_gemm_filter_segments(idx, mode);
+        p.ext = (unsigned long long*)ext;
+        p.ext_cnt = ext_cnt;
+        p.ext_cap = ext_cap;
+        p.eps2 = eps2;
         p.doc_base = (uint32_t)idx->doc_base;
         rc = dispatch_gemm(kind, mt, epi, cl, tv, tq, tql, p, pl.smem, idx->num_sms, st);
         if (rc != HS_OK) return rc;
@@ -782,6 +825,17 @@ int hs_dense_gemm(const hs_index* idx, const float* queries, int32_t B, int64_t 
     HS_REQUIRE(cos != nullptr && cos_ld >= doc_hi - doc_lo, "hs_dense_gemm: cos is null or cos_ld < doc range");
     return gemm_run(idx, queries, B, ld_q, mode, doc_lo, doc_hi, workspace, workspace_bytes, kEpiStore, cos, cos_ld,
                     nullptr, nullptr, 0, nullptr, stats_enc, stream, "hs_dense_gemm");
+}
+
+int hs_dense_gemm_ext(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t doc_lo,
+                      int64_t doc_hi, void* workspace, size_t workspace_bytes, float* cos, int64_t cos_ld,
+                      uint32_t* stats_enc, uint64_t* ext, uint32_t* ext_cnt, int32_t ext_cap, double eps, void* stream) {
+    HS_REQUIRE(cos != nullptr && cos_ld >= doc_hi - doc_lo, "hs_dense_gemm_ext: cos is null or cos_ld < doc range");
+    HS_REQUIRE(ext != nullptr && ext_cnt != nullptr && ext_cap > 0 && eps >= 0.0 && stats_enc != nullptr,
+               "hs_dense_gemm_ext: bad extreme-candidate buffers");
+    return gemm_run(idx, queries, B, ld_q, mode, doc_lo, doc_hi, workspace, workspace_bytes, kEpiStore, cos, cos_ld,
+                    nullptr, nullptr, 0, nullptr, stats_enc, stream, "hs_dense_gemm_ext", ext, ext_cnt, ext_cap,
+                    (float)(2.0 * eps));
 }
 
 int32_t hs_dense_gemm_filter_segments(const hs_index* idx, int32_t mode) {

@@ -248,7 +248,8 @@ __device__ __forceinline__ float fuse_score(const FuseParams& p, const FuseConst
 // exact key of each block.  The k-th largest of those maxima is attained by k DISTINCT docs, hence it is
 // a valid lower bound on the k-th best key of the whole shard -- and for k = 100 of 1024 maxima it sits
 // around the top 0.1 % of all docs, so the main pass rejects ~99.9 % of the elements with two FMAs.
-constexpr int kBoundBlocks = 1024;             // at most; smaller shards sample 512 or 256 blocks (bound_blocks_for)
+constexpr int kBoundBlocks = 1024;             // at most; smaller shards sample 512 or 256 blocks.  4096 blocks were
+                                               // measured: the larger sampling pass costs more than the tighter bound saves
 constexpr int kBoundDocs = 128;
 
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
@@ -584,6 +585,125 @@ __global__ void __launch_bounds__(kThreads) cand_select_kernel(const uint64_t* _
     for (int i = tid; i < k_out; i += kThreads) out[(int64_t)b * k_out + i] = sel.buf[i];
 }
 
+// ---- exact verification of an approximate dense scan ("screen with the tensor cores, verify in the conformance order") ---------
+// The bf16 GEMM gives every cosine within eps of the exact (float64-accumulated) value.  Two small kernels turn the
+// approximate hybrid ranking into the EXACT one:
+//   verify_stats_kernel  the exact global min / max cosine: only docs whose approximate score lies within 2 eps of the
+//                        approximate extreme can attain it; the GEMM epilogue listed (a superset of) them per segment
+//   verify_topk_kernel   the approximate select returned k' > k keys; their cosines are recomputed exactly, the fused score
+//                        re-evaluated with the reference's rounding steps and the list re-sorted.  A doc outside the list
+//                        has an exact fused score <= (k'-th approximate score) + delta, delta = |w_a| eps / range: if the
+//                        k-th exact score clears that bound the top k is provably the exact one, else the query is flagged
+//                        and the caller redoes it in the exact mode.
+struct VerifyParams {
+    const float* v;          // [n, ld] float32 rows
+    const float* vnorm;      // [n]
+    const float* q;          // [B, ld_q]
+    int64_t n, ld, ld_q;
+    int dim;
+    uint32_t doc_base;
+};
+
+constexpr int kVerifyList = 512;
+
+__global__ void __launch_bounds__(kThreads) verify_stats_kernel(const VerifyParams vp, const uint64_t* __restrict__ ext,
+                                                                const uint32_t* __restrict__ ext_cnt, int n_seg, int cap,
+                                                                float eps2, uint32_t* __restrict__ stats,
+                                                                int32_t* __restrict__ flags) {
+    __shared__ uint32_t lst[2][kVerifyList];         // shard-local docs that can attain the max (0) / min (1)
+    __shared__ int cnt[2];
+    __shared__ uint32_t best[2];                     // encoded exact max / min
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 2) {
+        cnt[tid] = 0;
+        best[tid] = tid == 0 ? 0u : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    const float amx = hs_dec_f32(stats[b * 4 + HS_STAT_MAX_A]), amn = hs_dec_f32(stats[b * 4 + HS_STAT_MIN_A]);
+    if (!(amn <= amx)) return;                       // the shard holds no doc: nothing to verify
+    int over = 0;
+    for (int s = tid; s < n_seg * 2; s += kThreads) {
+        const int side = s & 1;
+        uint32_t c = ext_cnt[(int64_t)b * n_seg * 2 + s];
+        if (c > (uint32_t)cap) {
+            over = 1;
+            c = (uint32_t)cap;
+        }
+        const uint64_t* e = ext + ((int64_t)b * n_seg * 2 + s) * cap;
+        for (uint32_t i = 0; i < c; ++i) {
+            const uint64_t key = e[i];
+            const float sc = hs_dec_f32((uint32_t)(key >> 32));
+            if (side == 0 ? sc >= amx - eps2 : sc <= amn + eps2) {
+                const int pos = atomicAdd(&cnt[side], 1);
+                if (pos < kVerifyList) lst[side][pos] = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu);
+                else over = 1;
+            }
+        }
+    }
+    over = __syncthreads_or(over);
+    const float* q = vp.q + (int64_t)b * vp.ld_q;
+    const float qn = hs_exact_norm_warp(q, vp.dim, lane);
+    for (int side = 0; side < 2; ++side) {
+        const int m = cnt[side] < kVerifyList ? cnt[side] : kVerifyList;
+        for (int i = warp; i < m; i += kThreads / 32) {
+            const uint32_t d = lst[side][i];
+            const float c = hs_exact_cos_warp(q, qn, vp.v + (int64_t)d * vp.ld, vp.vnorm[d], vp.dim, vp.ld, lane);
+            if (lane == 0) {
+                if (side == 0) atomicMax(&best[0], hs_enc_f32(c));
+                else atomicMin(&best[1], hs_enc_f32(c));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (over || cnt[0] == 0 || cnt[1] == 0) {
+            atomicOr(flags + b, 1);                  // a list overflowed: the exact extremes are not guaranteed
+        } else {
+            stats[b * 4 + HS_STAT_MAX_A] = best[0];
+            stats[b * 4 + HS_STAT_MIN_A] = best[1];
+        }
+    }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kThreads) verify_topk_kernel(const VerifyParams vp, const FuseParams p,
+                                                               const uint64_t* __restrict__ approx, int k_sel, int k_out,
+                                                               float eps, uint64_t* __restrict__ out,
+                                                               int32_t* __restrict__ flags) {
+    __shared__ uint64_t keys[KP];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const FuseConsts c = load_consts(p, b);
+    const float* q = vp.q + (int64_t)b * vp.ld_q;
+    const float qn = hs_exact_norm_warp(q, vp.dim, lane);
+    for (int i = tid; i < KP; i += kThreads) keys[i] = 0;
+    __syncthreads();
+    for (int i = warp; i < k_sel; i += kThreads / 32) {
+        const uint64_t key = approx[(int64_t)b * k_sel + i];
+        if (key == 0) continue;                                                    // warp-uniform
+        const uint32_t gid = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu);
+        const uint32_t d = gid - vp.doc_base;
+        const float cs = hs_exact_cos_warp(q, qn, vp.v + (int64_t)d * vp.ld, vp.vnorm[d], vp.dim, vp.ld, lane);
+        if (lane == 0) {
+            const float bv = p.b != nullptr ? p.b[(int64_t)b * p.ld + d] : 0.f;
+            keys[i] = hs_make_key(fuse_score(p, c, cs, bv), gid);
+        }
+    }
+    __syncthreads();
+    bitonic_sort_desc_n(keys, KP);
+    for (int i = tid; i < k_out; i += kThreads) out[(int64_t)b * k_out + i] = keys[i];
+    if (tid == 0) {
+        // soundness: every doc outside the approximate list scores at most (its last key) + delta exactly
+        const uint64_t last = approx[(int64_t)b * k_sel + k_sel - 1];
+        if (last != 0) {                                    // the list is full: there are docs outside it
+            const float f_last = hs_dec_f32((uint32_t)(last >> 32));
+            const float delta = c.const_a ? 0.f : fabsf(p.wa32) * eps / c.range_a * 1.001f + 1e-6f;
+            const uint64_t kth = keys[k_out - 1];
+            const float f_k = kth != 0 ? hs_dec_f32((uint32_t)(kth >> 32)) : -1e30f;
+            if (!(f_k > f_last + delta)) atomicOr(flags + b, 2);
+        }
+    }
+}
+
 int n_chunks_for(int64_t n) {
     int64_t c = (n + kChunkDocs - 1) / kChunkDocs;
     if (c < 1) c = 1;
@@ -730,6 +850,72 @@ int hs_cand_select(const uint64_t* cand, const uint32_t* cand_cnt, int32_t n_seg
         cand_select_kernel<512><<<B, kThreads, 0, st>>>(cand, cand_cnt, n_seg, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
     else
         cand_select_kernel<2048><<<B, kThreads, 0, st>>>(cand, cand_cnt, n_seg, cand_cap, extra_keys, n_extra, p, k_sel, k_out, out_keys, overflow);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+
+static int fill_verify(const hs_index* idx, const float* queries, int64_t ld_q, VerifyParams& vp, const char* who) {
+    HS_REQUIRE(idx != nullptr && queries != nullptr, "%s: null pointer", who);
+    if (idx->vectors == nullptr) {
+        hs_set_error("%s: index has no dense matrix", who);
+        return HS_ERR_STATE;
+    }
+    HS_REQUIRE(ld_q >= idx->dim, "%s: ld_q < dim", who);
+    vp.v = idx->vectors;
+    vp.vnorm = idx->vnorm;
+    vp.q = queries;
+    vp.n = idx->n_docs;
+    vp.ld = idx->ld;
+    vp.ld_q = ld_q;
+    vp.dim = idx->dim;
+    vp.doc_base = (uint32_t)idx->doc_base;
+    return HS_OK;
+}
+
+int hs_verify_stats(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, const uint64_t* ext,
+                    const uint32_t* ext_cnt, int32_t n_seg, int32_t ext_cap, double eps, uint32_t* stats_enc, int32_t* flags,
+                    void* stream) {
+    VerifyParams vp;
+    int rc = fill_verify(idx, queries, ld_q, vp, "hs_verify_stats");
+    if (rc != HS_OK) return rc;
+    if (B == 0 || idx->n_docs == 0) return HS_OK;
+    HS_REQUIRE(B > 0 && ext != nullptr && ext_cnt != nullptr && n_seg > 0 && ext_cap > 0 && stats_enc != nullptr &&
+                   flags != nullptr && eps >= 0.0, "hs_verify_stats: bad arguments");
+    verify_stats_kernel<<<B, kThreads, 0, (cudaStream_t)stream>>>(vp, ext, ext_cnt, n_seg, ext_cap, (float)(2.0 * eps),
+                                                                   stats_enc, flags);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
+}
+
+int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode, const float* b,
+                   const uint32_t* stats_enc, double w_a, double w_b, const uint64_t* approx_keys, int32_t k_sel,
+                   int32_t k_out, double eps, uint64_t* out_keys, int32_t* flags, void* stream) {
+    VerifyParams vp;
+    int rc = fill_verify(idx, queries, ld_q, vp, "hs_verify_topk");
+    if (rc != HS_OK) return rc;
+    if (B == 0) return HS_OK;
+    HS_REQUIRE(B > 0 && approx_keys != nullptr && out_keys != nullptr && flags != nullptr && stats_enc != nullptr &&
+                   k_out > 0 && k_out <= k_sel && k_sel <= 2048 && eps >= 0.0, "hs_verify_topk: bad arguments");
+    HS_REQUIRE(fuse_mode == HS_FUSE_SEARCHER || (fuse_mode == HS_FUSE_HYBRID_BM25 && b != nullptr),
+               "hs_verify_topk: fuse_mode must be SEARCHER or HYBRID_BM25 (with b)");
+    FuseParams p;
+    memset(&p, 0, sizeof(p));
+    p.b = b;
+    p.stats = stats_enc;
+    p.n = idx->n_docs;
+    p.ld = idx->n_docs;
+    p.doc_base = idx->doc_base;
+    p.mode = fuse_mode;
+    p.wa32 = (float)w_a;
+    p.wb32 = (float)w_b;
+    p.wa64 = w_a;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (k_sel <= 128)
+        verify_topk_kernel<128><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+    else if (k_sel <= 512)
+        verify_topk_kernel<512><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+    else
+        verify_topk_kernel<2048><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
     HS_LAUNCH_CHECK();
     return HS_OK;
 }

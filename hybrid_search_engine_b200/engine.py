@@ -55,6 +55,7 @@ class SearchEngine:
         self._bufs = {}
         self._pin_slot = 0         # which set of pinned staging buffers the uploads use (search_*_stream)
         self._pin_events = {}      # (slot, group) -> event recorded after the last H2D copy out of that staging set
+        self.phase_events = None   # bench.py sets a list to collect per-phase CUDA events of the verified chain
         self.launches = 0          # kernels launched by this engine (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------ buffers (never on the hot path twice)
@@ -243,18 +244,19 @@ class SearchEngine:
         return stats
 
     def fuse_topk(self, mode: int, a: torch.Tensor, b: Optional[torch.Tensor], stats: Optional[torch.Tensor],
-                  wa: float, wb: float, k: int, below: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """-> ranking keys int64-typed bit patterns [B, k] (merged across shards when sharded)."""
+                  wa: float, wb: float, k: int, below: Optional[torch.Tensor] = None, merge: bool = True,
+                  out: str = "keys") -> torch.Tensor:
+        """-> ranking keys int64-typed bit patterns [B, k] (merged across shards when sharded and ``merge``)."""
         B = a.shape[0]
         n = self.shard.n_docs
         ws_bytes = self.lib.hs_fuse_topk_workspace_bytes(n, B, k)
         ws = self._buf("topk_ws", (max(ws_bytes // 8, 1),), torch.int64)
-        keys = self._buf("keys", (B, k), torch.int64)
+        keys = self._buf(out, (B, k), torch.int64)
         check(self.lib.hs_fuse_topk(self.shard.handle, mode, ptr(a), ptr(b), ptr(stats), float(wa), float(wb),
                                     B, k, ptr(below), ptr(ws), ws_bytes, ptr(keys), stream_ptr(self.device)),
               "hs_fuse_topk")
         self.launches += 2 if n > 0 else 0
-        return self._merge_across(keys)
+        return self._merge_across(keys) if merge else keys
 
     def _merge_across(self, keys: torch.Tensor) -> torch.Tensor:
         """C1: all-gather of the per-shard key lists [B, k] + merge kernel; identity on a single shard."""
@@ -461,9 +463,59 @@ class SearchEngine:
         """BM25.search (bm25.py:129-142): raw float32 BM25 score, canonical tie order (BM25Plus with ``plus_delta``)."""
         return self._run(qb, k, HS_FUSE_RAW, 1.0, 0.0, False, True, None, plus_delta=plus_delta)
 
+    # ------------------------------------------------------------------ screen on the tensor cores, verify exactly
+    VERIFY_EXT_CAP = 64
+
+    def _verified_sub_batch(self, qd, nb, stats, bm, mode, wa, wb, k, flags, eps):
+        """One sub-batch of ``dense_mode="bf16_exact"``: bf16 GEMM (cos within eps) -> exact min / max from the listed
+        extreme candidates -> approximate select of k_sel > k docs -> exact re-scoring + re-sort + soundness check
+        (hs_verify_topk).  ``bm`` is produced by ``bm_fn(stats)`` between the scan and the statistics.  -> keys [nb, k]."""
+        m = _lib.HS_DENSE_BF16
+        n = self.shard.n_docs
+        st = stream_ptr(self.device)
+        marks = self.phase_events          # bench.py: a list -> one CUDA event per phase boundary of every sub-batch
+
+        def mark():
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
+        mark()
+        n_seg = self.lib.hs_dense_gemm_filter_segments(self.shard.handle, m)
+        cap = self.VERIFY_EXT_CAP
+        wsp, nbytes = self._gemm_ws(nb, m)
+        cos = self._buf("cos", (nb, n), torch.float32)
+        ext = self._buf("vext", (nb, n_seg, 2, cap), torch.int64)
+        ext_cnt = self._buf("vext_cnt", (nb, n_seg, 2), torch.int32)
+        ext_cnt.zero_()
+        check(self.lib.hs_dense_gemm_ext(self.shard.handle, ptr(qd), nb, qd.stride(0), m, 0, n, wsp, nbytes, ptr(cos), n,
+                                         ptr(stats), ptr(ext), ptr(ext_cnt), cap, float(eps), st), "hs_dense_gemm_ext")
+        mark()
+        b = bm(stats) if callable(bm) else bm
+        mark()
+        check(self.lib.hs_verify_stats(self.shard.handle, ptr(qd), nb, qd.stride(0), ptr(ext), ptr(ext_cnt), n_seg, cap,
+                                       float(eps), ptr(stats), ptr(flags), st), "hs_verify_stats")
+        stats = self._exchange_stats(stats, nb)
+        k_sel = 512 if k <= 256 else HS_TOPK_MAX
+        approx = self.fuse_topk(mode, cos, b, stats, wa, wb, k_sel, merge=False, out="vkeys")
+        keys = self._buf("keys", (nb, k), torch.int64)
+        check(self.lib.hs_verify_topk(self.shard.handle, ptr(qd), nb, qd.stride(0), mode, ptr(b), ptr(stats), float(wa),
+                                      float(wb), ptr(approx), k_sel, k, float(eps), ptr(keys), ptr(flags), st),
+              "hs_verify_topk")
+        self.launches += 2 * self._gemm_passes(nb, m) + 3
+        keys = self._merge_across(keys)
+        mark()
+        return keys
+
     def _run(self, qb, k, mode, wa, wb, use_dense, use_bm25, dense_mode, lex=None, plus_delta=None):
         B = len(qb)
         out_s, out_i = [], []
+        verify = use_dense and (dense_mode or self.dense_mode) == "bf16_exact"
+        if verify and (mode == HS_FUSE_RAW or k > 1024 or self.shard.n_docs == 0):
+            verify, dense_mode = False, "exact"
+        if verify:
+            flags = torch.zeros(max(B, 1), dtype=torch.int32, device=self.device)
+            eps = _lib.VERIFY_EPS["bf16_exact"]
         with torch.cuda.device(self.device):
             # ONE upload of the whole batch before the sub-batch loop; the loop only slices device tensors (the
             # staging buffers are never rewritten while a sub-batch that reads them is still queued)
@@ -473,9 +525,9 @@ class SearchEngine:
                 nb = e - s
                 stats = self._stats(nb)
                 cos = bm = None
-                if use_dense:
+                if use_dense and not verify:
                     cos = self.dense_scan(qd_all[s:e], stats, dense_mode)
-                if use_bm25:
+                if use_bm25 and not verify:
                     qt, qi, qo, n_tok = terms_all[bi]
                     bm = self.bm25_score(qt, qi, qo, nb, stats, n_tok, plus_delta=plus_delta)
                 if lex is not None:
@@ -488,16 +540,37 @@ class SearchEngine:
                     check(self.lib.hs_stats_fold_minmax(ptr(bm), self.shard.n_docs, nb, 3, 2, ptr(stats),
                                                         stream_ptr(self.device)), "hs_stats_fold_minmax")
                     self.launches += 1
-                if mode != HS_FUSE_RAW:
-                    stats = self._exchange_stats(stats, nb)
-                a, b = (cos, bm) if use_dense else (bm, None)
-                keys = self._select(mode, a, b, stats, wa, wb, k)
+                if verify:
+                    if use_bm25:
+                        qt, qi, qo, n_tok = terms_all[bi]
+                        bm = (lambda st_, a=(qt, qi, qo, nb, n_tok): self.bm25_score(a[0], a[1], a[2], a[3], st_, a[4]))
+                    keys = self._verified_sub_batch(qd_all[s:e], nb, stats, bm, mode, wa, wb, k, flags[s:e], eps)
+                else:
+                    if mode != HS_FUSE_RAW:
+                        stats = self._exchange_stats(stats, nb)
+                    a, b = (cos, bm) if use_dense else (bm, None)
+                    keys = self._select(mode, a, b, stats, wa, wb, k)
                 sc, ids = self.unpack(keys)
                 out_s.append(sc.clone() if e < B or s > 0 else sc)
                 out_i.append(ids.clone() if e < B or s > 0 else ids)
-        if len(out_s) == 1:
-            return out_s[0], out_i[0]
-        return torch.cat(out_s), torch.cat(out_i)
+        sc, ids = (out_s[0], out_i[0]) if len(out_s) == 1 else (torch.cat(out_s), torch.cat(out_i))
+        if verify:
+            # queries whose verification could not PROVE the result (a candidate list overflowed, or the k-th exact score
+            # does not clear the bound on the docs outside the candidate list) are redone in the exact mode
+            if self.group is not None and self.world > 1:
+                from .parallel import all_reduce_
+                all_reduce_(flags, "max", self.group)
+            bad = torch.nonzero(flags[:B]).flatten().cpu().tolist()
+            self.verify_fallbacks = getattr(self, "verify_fallbacks", 0) + len(bad)
+            if bad:
+                sc, ids = sc.clone(), ids.clone()
+                sub = QueryBatch(vectors=None if qb.vectors is None else qb.vectors[bad],
+                                 term_ids=None if qb.term_ids is None else [qb.term_ids[i] for i in bad])
+                lx = None if lex is None else lex[bad]
+                s2, i2 = self._run(sub, k, mode, wa, wb, use_dense, use_bm25, "exact", lex=lx, plus_delta=plus_delta)
+                idx = torch.tensor(bad, dtype=torch.int64, device=self.device)
+                sc[idx], ids[idx] = s2, i2
+        return sc, ids
 
     # ------------------------------------------------------------------ one hybrid step on device tensors
     def hybrid_step_device(self, qd, qt, qi, qo, B: int, n_tokens: int, k: int, ws: float, wl: float,

@@ -123,6 +123,30 @@ size_t hs_dense_gemm_workspace_bytes(const hs_index* idx, int32_t B, int32_t mod
 int hs_dense_gemm(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t doc_lo,
                   int64_t doc_hi, void* workspace, size_t workspace_bytes, float* cos, int64_t cos_ld,
                   uint32_t* stats_enc, void* stream);
+/* hs_dense_gemm that also lists, per query and (CTA, epilogue group) segment, the docs whose score is within 2 * eps of
+ * the segment's running max / min: ext uint64 [B, n_seg, 2, ext_cap] keys (score, shard-local doc; hi side then lo side),
+ * ext_cnt uint32 [B, n_seg, 2] (zero first; > ext_cap = overflow).  eps bounds |score - exact cosine| of the mode
+ * (bf16: 2^-8 by Cauchy-Schwarz + accumulation slack = 4.2e-3).  Feeds hs_verify_stats. */
+int hs_dense_gemm_ext(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t doc_lo,
+                      int64_t doc_hi, void* workspace, size_t workspace_bytes, float* cos, int64_t cos_ld,
+                      uint32_t* stats_enc, uint64_t* ext, uint32_t* ext_cnt, int32_t ext_cap, double eps, void* stream);
+/* Exact verification of an approximate scan (screen on the tensor cores, verify in the conformance order; no reference
+ * counterpart -- it is what lets the bf16 GEMM return the reference's exact ranking):
+ *   hs_verify_stats  replaces stats slots MIN_A / MAX_A by the EXACT min / max cosine of the shard (utils.py:67-68),
+ *                    recomputing only the listed candidates; flags[b] |= 1 if a list overflowed
+ *   hs_verify_topk   approx_keys [B, k_sel] = the best k_sel docs by the fused score computed from the approximate
+ *                    cosine under the exact stats; their cosines are recomputed exactly (utils.py:28-54 in the
+ *                    conformance order), the fused score re-evaluated (b = the BM25 vector for HS_FUSE_HYBRID_BM25), the
+ *                    list re-sorted: out_keys [B, k_out].  flags[b] |= 2 unless the k_out-th exact score exceeds the
+ *                    k_sel-th approximate score by more than |w_a| * eps / (max - min): then no doc outside the list
+ *                    can belong to the top k_out and the result is provably the exact mode's; flagged queries must be
+ *                    redone in an exact mode by the caller. */
+int hs_verify_stats(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, const uint64_t* ext,
+                    const uint32_t* ext_cnt, int32_t n_seg, int32_t ext_cap, double eps, uint32_t* stats_enc, int32_t* flags,
+                    void* stream);
+int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode, const float* b,
+                   const uint32_t* stats_enc, double w_a, double w_b, const uint64_t* approx_keys, int32_t k_sel,
+                   int32_t k_out, double eps, uint64_t* out_keys, int32_t* flags, void* stream);
 /* the same GEMM with the select's pre-filter fused into its epilogue (pure-semantic retrieval: Searcher.search with
  * lexical weight 0, multi_stage stage 1, pipelines.py:474-481): nothing is stored; every (query, doc) cosine >=
  * thr[b] (NULL: all) is appended as a ranking key to the query's candidate lists.  No atomics: each (CTA, epilogue

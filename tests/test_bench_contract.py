@@ -53,7 +53,7 @@ def test_bench_runs_on_a_small_corpus_and_reproduces_the_committed_digest():
     per-kernel rooflines, the plugin-API e2e leg, ids identical to the exact mode, and the exact-mode digest of the fixed
     64-query batch equal to the constant in tests/golden/bench_digests.json (generated at N = 1)."""
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--n-docs", "300000", "--vocab", "50000",
-                          "--batch", "16", "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--dense-mode", "tf32x3"],
+                          "--batch", "16", "--steps", "3", "--warmup", "3", "--no-cpu-baseline"],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]

@@ -168,3 +168,56 @@ def test_tf32x3_hybrid_ids_match_exact_up_to_near_ties(hs):
         for a, c in zip(i_t[b], i_e[b]):
             assert a == c or abs(sc[int(a)] - sc[int(c)]) <= 4 * np.spacing(np.float32(abs(sc[int(c)]))), (b, a, c)
     print(f"tf32x3 hybrid: {same}/{B} queries with identical top-100 ids, the rest differ only inside 4-ulp ties")
+
+
+@pytest.mark.parametrize("B,k", [(300, 100), (17, 10), (130, 400)])
+def test_bf16_exact_mode_is_bit_identical_to_exact(hs, B, k):
+    """dense_mode="bf16_exact": bf16 tensor-core screen + verification in the conformance order returns the ids AND float32
+    scores of the exact mode (== oracle) for hybrid_bm25, semantic-only and searcher-with-lexical-vector fusion; the
+    count of queries that needed the exact fallback is printed (0 expected on this corpus)."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=300_000, vocab=50_000, dim=96)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, torch.device("cuda:0"))
+    v = shard.vectors
+    v[1000:1050] = v[2000:2050]                          # duplicate rows: exact ties near the top
+    v[17] = 0.0
+    shard.set_dense(v[:, :spec.dim].clone())
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    qv = synth.query_embeddings(spec, 0, B)
+    qv[2] = v[1003, :spec.dim].cpu().numpy() * 0.5
+    if B > 5:
+        qv[5] = 0.0                                      # zero query: every cosine 0 -> constant -> ones
+    qb = QueryBatch(vectors=qv, term_ids=synth.query_terms(spec, 0, B, th).tolist())
+    eng = SearchEngine(shard, max_batch=256)
+    got = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="bf16_exact")]
+    eng.max_batch = 8
+    want = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="exact")]
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    eng.max_batch = 256
+    got = [t.cpu().numpy().copy() for t in eng.search_semantic(QueryBatch(vectors=qv), k, 0.7, dense_mode="bf16_exact")]
+    eng.max_batch = 8
+    want = [t.cpu().numpy().copy() for t in eng.search_semantic(QueryBatch(vectors=qv), k, 0.7, dense_mode="exact")]
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    lex = torch.rand((min(B, 40), spec.n_docs), device="cuda", dtype=torch.float32)
+    qs = QueryBatch(vectors=qv[:lex.shape[0]])
+    eng.max_batch = 256
+    got = [t.cpu().numpy().copy() for t in eng.search_searcher(qs, lex, k, 0.7, 0.3, dense_mode="bf16_exact")]
+    eng.max_batch = 8
+    want = [t.cpu().numpy().copy() for t in eng.search_searcher(qs, lex, k, 0.7, 0.3, dense_mode="exact")]
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    print(f"bf16_exact: {getattr(eng, 'verify_fallbacks', 0)} of {2 * B + lex.shape[0]} queries fell back to the exact mode")
+
+
+def test_bf16_exact_pipeline_matches_oracle_on_real_text(hs):
+    """create_pipeline("hybrid_bm25", dense_mode="bf16_exact") on the T1 corpus (ties, empty docs, zero vectors) == oracle."""
+    from tests.golden_cases import load_case
+    c = load_case("t1_mid")
+    ix = orc.build_index(c.docs, c.emb)
+    p = hs.create_pipeline("hybrid_bm25", dense_mode="bf16_exact")
+    p.index(c.docs, embeddings=c.emb)
+    res = p.search_many(c.queries, top_k=50, query_vectors=c.q_emb)
+    for qi, q in enumerate(c.queries):
+        ids, sc, _ = orc.search_hybrid_bm25(ix, q, c.q_emb[qi], 50)
+        assert [r["doc_id"] for r in res[qi].results] == ids.tolist(), q
+        assert np.array_equal(np.array([r["score"] for r in res[qi].results], np.float32), sc), q
