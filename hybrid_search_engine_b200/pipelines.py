@@ -11,7 +11,9 @@ MiniLM inside Indexer/Searcher, indexer.py:91, core.py:134):
 * ``encoder=``      object with ``encode(list[str]) -> float32 [n, d]`` (defaults to
                     sentence-transformers ``all-MiniLM-L6-v2`` if installed, else a clear error)
 * ``index_build=``  "host" | "device": where ``BM25.fit`` tokenises and builds the CSR (index_build.py)
-* ``device=``       CUDA device of the shard, ``dense_mode=`` "exact" | "fp32" | "bf16" (tcgen05 GEMM)
+* ``device=``       CUDA device of the shard, ``dense_mode=`` "exact" | "fp32" | "tf32x3" | "bf16" | "bf16_exact"
+                    (the last three run on the tensor cores; "bf16_exact" = bf16 screen + exact verification,
+                    results of "exact" at large query batches)
 * ``index(documents, source_paths=None, embeddings=None)``  precomputed document vectors
 * ``search(query, top_k, query_vector=None)``               precomputed query vector
 * ``search_many(queries, top_k, query_vectors=None)``       one batched launch chain for B queries
