@@ -368,6 +368,7 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
         float inv_qn[MT], mn[MT], mx[MT], thr[MT];
         uint32_t n_app[MT];                                       // FILTER: keys appended to this thread's segments
         uint32_t n_hi[MT], n_lo[MT];                              // STORE + ext: entries of the extreme-candidate lists
+        float g_hi[MT], g_lo[MT], pub_hi[MT], pub_lo[MT];         // ... and the query's max / min over ALL CTAs so far
         bool active[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -378,6 +379,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             mx[mt] = __int_as_float(0xff800000);
             n_app[mt] = 0;
             n_hi[mt] = n_lo[mt] = 0;
+            g_hi[mt] = pub_hi[mt] = __int_as_float(0xff800000);
+            g_lo[mt] = pub_lo[mt] = __int_as_float(0x7f800000);
             thr[mt] = (EPI == kEpiFilter && active[mt] && p.thr != nullptr) ? __ldg(p.thr + p.b0 + b)
                                                                              : __int_as_float(0xff800000);
         }
@@ -402,6 +405,30 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             mbar_wait(&tmem_full[buf], (uint32_t)((tile_i >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ndoc = (int)((p.d1 - doc0 < kTileN) ? (p.d1 - doc0) : kTileN);
+            if constexpr (EPI == kEpiStore) {
+                // extreme-candidate lists: the window hangs off the query's max / min over ALL CTAs so far (published through
+                // the stats slots once per tile), not off this thread's own running extreme -- a per-thread window triggered
+                // in ~4 % of the chunks per thread, i.e. in most chunks per WARP (32 queries), doubling the epilogue
+                if (p.ext != nullptr) {
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        if (active[mt]) {
+                            uint32_t* st = p.stats + (int64_t)(p.b0 + mt * kTileM + etid) * 4;
+                            if (mx[mt] > pub_hi[mt]) {
+                                atomicMax(st + HS_STAT_MAX_A, hs_enc_f32(mx[mt]));
+                                pub_hi[mt] = mx[mt];
+                            }
+                            if (mn[mt] < pub_lo[mt]) {
+                                atomicMin(st + HS_STAT_MIN_A, hs_enc_f32(mn[mt]));
+                                pub_lo[mt] = mn[mt];
+                            }
+                            // fmaxf / fminf drop the NaN an untouched slot decodes to
+                            g_hi[mt] = fmaxf(g_hi[mt], hs_dec_f32(__ldcg(st + HS_STAT_MAX_A)));
+                            g_lo[mt] = fminf(g_lo[mt], hs_dec_f32(__ldcg(st + HS_STAT_MIN_A)));
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
                 const int nrow_raw = p.nq_valid - mt * kTileM - e * 32;                  // live queries of this warp
@@ -455,20 +482,22 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                         if (p.ext != nullptr && active[mt]) {      // warp-uniform on p.ext; both tests are rare after the first tiles
                             unsigned long long* lst = p.ext + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
                                                                (blockIdx.x * kEpiGroups + grp)) * 2 * p.ext_cap;
-                            if (cmx >= mx[mt] - p.eps2) {
+                            const float ref_hi = fmaxf(mx[mt], g_hi[mt]) - p.eps2;      // <= (final global max) - eps2
+                            const float ref_lo = fminf(mn[mt], g_lo[mt]) + p.eps2;
+                            if (cmx >= ref_hi) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
-                                    if (j < nvalid && v[j] >= mx[mt] - p.eps2) {
+                                    if (j < nvalid && v[j] >= ref_hi) {
                                         if (n_hi[mt] < (uint32_t)p.ext_cap)
                                             lst[n_hi[mt]] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
                                         ++n_hi[mt];
                                     }
                                 }
                             }
-                            if (cmn <= mn[mt] + p.eps2) {
+                            if (cmn <= ref_lo) {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j) {
-                                    if (j < nvalid && v[j] <= mn[mt] + p.eps2) {
+                                    if (j < nvalid && v[j] <= ref_lo) {
                                         if (n_lo[mt] < (uint32_t)p.ext_cap)
                                             lst[p.ext_cap + n_lo[mt]] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
                                         ++n_lo[mt];

@@ -80,7 +80,7 @@ __device__ __forceinline__ void bitonic_sort_desc_n(uint64_t* a, int n) {
 // bound", still a superset of (global top k) restricted to the range, which is all the merge needs.
 template <int KP>
 struct Selector {
-    static constexpr int CAP = (KP <= 128) ? 8 * KP : 2 * KP;
+    static constexpr int CAP = (KP <= 128) ? 8 * KP : (KP <= 256 ? 4 * KP : 2 * KP);
     uint64_t buf[CAP];
     uint64_t thr;   // keys <= thr cannot be in the top k any more
     int cnt;        // next free slot (>= KP: slots [0, KP) hold the current best)
@@ -704,10 +704,19 @@ __global__ void __launch_bounds__(kThreads) verify_topk_kernel(const VerifyParam
     }
 }
 
-int n_chunks_for(int64_t n) {
-    int64_t c = (n + kChunkDocs - 1) / kChunkDocs;
+// CTAs (= candidate lists of k keys) per query.  Every list costs k keys of output, a sort and a slot in the merge,
+// whatever its doc range: on a small shard with a large k (doc-sharded runs, the 256 / 512-key lists of the verified
+// mode) 296 lists of a few thousand docs made the select chain a FIXED cost.  So: at least 64 k docs per list, but
+// enough CTAs over the batch to fill the GPU twice, at most 296, at least 4096 docs each.
+int n_chunks_for(int64_t n, int B, int k) {
+    int64_t cap = (n + kChunkDocs - 1) / kChunkDocs;
+    if (cap > kMaxChunks) cap = kMaxChunks;
+    if (cap < 1) cap = 1;
+    int64_t c = n / ((int64_t)64 * (k > 0 ? k : 1));
+    const int64_t fill = (2 * kMaxChunks + (B > 0 ? B : 1) - 1) / (B > 0 ? B : 1);
+    if (c < fill) c = fill;
+    if (c > cap) c = cap;
     if (c < 1) c = 1;
-    if (c > kMaxChunks) c = kMaxChunks;
     return (int)c;
 }
 
@@ -725,6 +734,7 @@ int launch_merge(const uint64_t* keys, int n_lists, int B, int k, int64_t list_s
 int merge_dispatch(const uint64_t* keys, int n_lists, int B, int k, int64_t list_stride, int64_t query_stride,
                    uint64_t* out, cudaStream_t st) {
     if (k <= 128) return launch_merge<128>(keys, n_lists, B, k, list_stride, query_stride, out, st);
+    if (k <= 256) return launch_merge<256>(keys, n_lists, B, k, list_stride, query_stride, out, st);
     if (k <= 512) return launch_merge<512>(keys, n_lists, B, k, list_stride, query_stride, out, st);
     return launch_merge<2048>(keys, n_lists, B, k, list_stride, query_stride, out, st);
 }
@@ -735,7 +745,7 @@ extern "C" {
 
 size_t hs_fuse_topk_workspace_bytes(int64_t n_docs, int32_t B, int32_t k) {
     if (n_docs <= 0 || B <= 0 || k <= 0) return 0;
-    return ((size_t)B * n_chunks_for(n_docs) * (size_t)k + (size_t)B + (size_t)B * kBoundBlocks) * sizeof(uint64_t);
+    return ((size_t)B * n_chunks_for(n_docs, B, k) * (size_t)k + (size_t)B + (size_t)B * kBoundBlocks) * sizeof(uint64_t);
 }
 
 static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t fuse_mode, const float* a, const float* b,
@@ -773,7 +783,7 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
     p.doc_base = doc_base;
     p.mode = fuse_mode;
     p.k = k;
-    p.n_chunks = n_chunks_for(n_docs);
+    p.n_chunks = n_chunks_for(n_docs, B, k);
     p.wa32 = (float)w_a;   // numpy: float32 array * python float -> float32(w)
     p.wb32 = (float)w_b;
     p.wa64 = w_a;
@@ -795,6 +805,8 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
     }
     if (k <= 128)
         fuse_topk_kernel<128><<<grid, kThreads, 0, st>>>(p);
+    else if (k <= 256)
+        fuse_topk_kernel<256><<<grid, kThreads, 0, st>>>(p);
     else if (k <= 512)
         fuse_topk_kernel<512><<<grid, kThreads, 0, st>>>(p);
     else
@@ -912,6 +924,8 @@ int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     if (k_sel <= 128)
         verify_topk_kernel<128><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+    else if (k_sel <= 256)
+        verify_topk_kernel<256><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
     else if (k_sel <= 512)
         verify_topk_kernel<512><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
     else

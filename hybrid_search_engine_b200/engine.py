@@ -56,6 +56,7 @@ class SearchEngine:
         self._pin_slot = 0         # which set of pinned staging buffers the uploads use (search_*_stream)
         self._pin_events = {}      # (slot, group) -> event recorded after the last H2D copy out of that staging set
         self.phase_events = None   # bench.py sets a list to collect per-phase CUDA events of the verified chain
+        self.verify_wide = False   # bf16_exact: re-score 512 instead of 256 candidates per query (set after fallbacks)
         self.launches = 0          # kernels launched by this engine (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------ buffers (never on the hot path twice)
@@ -496,7 +497,10 @@ class SearchEngine:
         check(self.lib.hs_verify_stats(self.shard.handle, ptr(qd), nb, qd.stride(0), ptr(ext), ptr(ext_cnt), n_seg, cap,
                                        float(eps), ptr(stats), ptr(flags), st), "hs_verify_stats")
         stats = self._exchange_stats(stats, nb)
-        k_sel = 512 if k <= 256 else HS_TOPK_MAX
+        # candidates re-scored per query: the smaller the list the cheaper the select, but the k-th exact score must clear
+        # the bound on the docs outside it (else the query falls back): 2.56 k by default, widened for good once more than
+        # 5 % of a call's queries fell back (see _run)
+        k_sel = (256 if k <= 100 and not self.verify_wide else 512) if k <= 256 else HS_TOPK_MAX
         approx = self.fuse_topk(mode, cos, b, stats, wa, wb, k_sel, merge=False, out="vkeys")
         keys = self._buf("keys", (nb, k), torch.int64)
         check(self.lib.hs_verify_topk(self.shard.handle, ptr(qd), nb, qd.stride(0), mode, ptr(b), ptr(stats), float(wa),
@@ -562,6 +566,8 @@ class SearchEngine:
                 all_reduce_(flags, "max", self.group)
             bad = torch.nonzero(flags[:B]).flatten().cpu().tolist()
             self.verify_fallbacks = getattr(self, "verify_fallbacks", 0) + len(bad)
+            if len(bad) > max(1, B // 20):
+                self.verify_wide = True
             if bad:
                 sc, ids = sc.clone(), ids.clone()
                 sub = QueryBatch(vectors=None if qb.vectors is None else qb.vectors[bad],
