@@ -535,7 +535,7 @@ def run_ours(args):
     # ---------------------------------------------------------------- end to end with host inputs / host outputs
     host_batches = [batch_of(args.warmup + s) for s in range(args.steps)]
     warm_batches = [batch_of(s) for s in range(3)]
-    depth = 2 if world <= 4 else 1
+    depth = 2      # two batches in flight: the host prepares / uploads batch i+1 while batch i runs
     e2e_note = None
     if wl == "hybrid":
         for _ in eng.search_hybrid_bm25_stream(warm_batches, k, 0.6, 0.4, depth=depth):
@@ -673,7 +673,7 @@ def run_ours(args):
         sel_bytes = (8 if wl == "hybrid" else 4) * n_shard * B
         sname = "fuse_blockmax + fuse_bound + fuse_topk + topk_merge + keys_unpack"
         if args.dense_mode == "bf16_exact" and wl == "hybrid":
-            sname = "verify_stats + fuse_blockmax + fuse_bound + fuse_topk (k' = 512) + topk_merge + verify_topk + keys_unpack"
+            sname = "verify_stats + fuse_blockmax + fuse_bound + fuse_topk (k' = 256) + topk_merge + verify_topk + keys_unpack"
         kernels.append({"name": sname + (" (+ C2/C1 exchange)" if world > 1 else ""),
                         "ms_per_step": select_ms, "alg_bytes_per_step": sel_bytes, "hbm_GBps": sel_bytes / select_ms / 1e6,
                         "frac_hbm": sel_bytes / select_ms / 1e6 / hbm_peak})

@@ -115,30 +115,37 @@ class SearchEngine:
     def upload_terms_split(self, term_ids: Sequence[Sequence[int]], per: int):
         """One upload for the whole batch, sliced on the device into sub-batches of ``per`` queries:
         -> [(q_terms int32 [T_s], q_idf float64 [T_s], q_off int32 [nb_s + 1] (rebased to 0), T_s), ...]."""
+        from itertools import chain
         idf = self.shard.idf_host
         df = self.shard.df_host
         nq = len(term_ids)
-        flat: List[int] = []
+        # flatten with numpy (the serving loop runs this once per batch, next to a ~1.5 ms GPU step at 8 ranks)
+        lens = np.fromiter(map(len, term_ids), dtype=np.int64, count=nq)
+        allt = np.fromiter(chain.from_iterable(term_ids), dtype=np.int64, count=int(lens.sum()))
+        # bm25.py:100 -- terms that are in no document have no idf entry and are skipped
+        keep = (allt >= 0) & (allt < len(df))
+        keep[keep] = df[allt[keep]] > 0
+        arr = allt[keep]
+        qend = np.cumsum(lens)
+        kept_before = np.concatenate([[0], np.cumsum(keep)])                 # kept tokens before position i
+        tok_end = kept_before[qend] if nq else np.zeros(0, np.int64)         # kept tokens up to the end of query q
+        T = int(arr.size)
         offs: List[int] = []            # concatenated, each sub-batch starting again at 0
         cuts = []                       # (token start, offset start, nb) per sub-batch
         for s in range(0, max(nq, 1), per):
-            t0 = len(flat)
-            cuts.append((t0, len(offs), min(nq, s + per) - s))
+            e_ = min(nq, s + per)
+            t0 = int(tok_end[s - 1]) if s > 0 else 0
+            cuts.append((t0, len(offs), e_ - s))
             offs.append(0)
-            for ids in term_ids[s:s + per]:
-                # bm25.py:100 -- terms that are in no document have no idf entry and are skipped
-                flat.extend(int(t) for t in ids if 0 <= int(t) < len(df) and df[int(t)] > 0)
-                offs.append(len(flat) - t0)
-        T = len(flat)
+            offs.extend((tok_end[s:e_] - t0).tolist())
         self._pin_wait("qt")
         pin_t = self._pinned("qt", (max(T, 1),), torch.int32)
         pin_i = self._pinned("qi", (max(T, 1),), torch.float64)
         pin_o = self._pinned("qo", (len(offs),), torch.int32)
         if T:
-            arr = np.asarray(flat, dtype=np.int64)
             pin_t[:T].copy_(torch.from_numpy(arr.astype(np.int32)))
             pin_i[:T].copy_(torch.from_numpy(idf[arr]))
-        pin_o.copy_(torch.tensor(offs, dtype=torch.int32))
+        pin_o.copy_(torch.from_numpy(np.asarray(offs, dtype=np.int32)))
         d_t = self._buf("qt", (max(T, 1),), torch.int32)
         d_i = self._buf("qi", (max(T, 1),), torch.float64)
         d_o = self._buf("qo", (len(offs),), torch.int32)

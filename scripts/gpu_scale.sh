@@ -1,4 +1,4 @@
-# usage: bash scripts/gpu_scale.sh N [tag]   -- bench.py at N ranks: default hybrid workload (+ configs 3/4/5 when N == 8 or N == 1)
+# usage: bash scripts/gpu_scale.sh N [tag] [all]   -- bench.py at N ranks: default hybrid workload (+ 8-query point and configs 3/4/5 with "all")
 N=$1; TAG=${2:-r2}
 mkdir -p gpurun_out
 run() {  # name, extra args
@@ -12,7 +12,7 @@ run() {  # name, extra args
   echo "== $name n=$N rc=$?"; tail -c 600 gpurun_out/${TAG}_${name}_n$N.json; echo; tail -n 2 gpurun_out/${TAG}_${name}_n$N.err | cut -c1-300
 }
 run hybrid --steps 20 --warmup 5
-if [ "$N" = "8" ] || [ "$N" = "1" ]; then
+if [ "$3" = "all" ]; then
   run hybrid_b8 --steps 20 --warmup 5 --batch 8 --dense-mode fp32 --no-extras --no-cpu-baseline
   run bm25 --workload bm25 --steps 10 --warmup 3
   run multi_stage --workload multi_stage --steps 5 --warmup 3
