@@ -52,7 +52,7 @@ UNIT = "queries/s"
 WORKLOADS = {
     # name: (metric, defaults)
     "hybrid": ("hybrid_bm25 queries/sec @10M docs 384-d top-100",
-               dict(n_docs=10_000_000, dim=384, batch=128, top_k=100, dense_mode="bf16_exact")),
+               dict(n_docs=10_000_000, dim=384, batch=256, top_k=100, dense_mode="bf16_exact")),
     "bm25": ("bm25 queries/sec @50M docs top-100 (BASELINE config 3)",
              dict(n_docs=50_000_000, dim=384, batch=32, top_k=100, dense_mode="fp32")),
     "multi_stage": ("multi_stage stages 1-2 queries/sec @10M docs 768-d bf16, dense top-100 -> BM25 top-20 (BASELINE config 4)",
@@ -347,6 +347,14 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- ours
+class _Marks(list):
+    """Phase-boundary CUDA events of one sub-batch (engine.phase_events) + named marks inside the last phase."""
+
+    def __init__(self):
+        super().__init__()
+        self.extra = []
+
+
 def digest_of(ids, sc):
     return hashlib.sha256(np.ascontiguousarray(ids, dtype=np.int64).tobytes()
                           + np.ascontiguousarray(sc, dtype=np.float32).tobytes()).hexdigest()
@@ -427,7 +435,7 @@ def run_ours(args):
             stats = eng._stats(nb)
             if args.dense_mode == "bf16_exact":      # screen (bf16 GEMM) + exact verification: one fused chain
                 qt, qi, qo, n_tok = terms[bi]
-                eng.phase_events = [] if timers is not None else None
+                eng.phase_events = _Marks() if timers is not None else None
                 keys = eng._verified_sub_batch(qd[s:s + nb], nb, stats,
                                                lambda st_: eng.bm25_score(qt, qi, qo, nb, st_, n_tok), 2, 0.6, 0.4, k,
                                                vflags[s:s + nb], _lib.VERIFY_EPS["bf16_exact"])
@@ -519,11 +527,16 @@ def run_ours(args):
     launches = eng.launches - launches0
     dev_ms = ev0.elapsed_time(ev1)
     parts = [0.0, 0.0, 0.0]
+    chain_ms = {}
     if timers:
         per_step = len(timers) / args.steps
         for e in timers:
             for j in range(3):
                 parts[j] += e[j].elapsed_time(e[j + 1])
+            prev = e[2]
+            for name, evx in list(getattr(e, "extra", [])) + [("exchange_keys", e[3])]:
+                chain_ms[name] = chain_ms.get(name, 0.0) + prev.elapsed_time(evx) / args.steps
+                prev = evx
         parts = [p / args.steps for p in parts]                 # ms per STEP for dense / bm25 / select chain
     t = torch.tensor([dev_ms] + parts, dtype=torch.float64, device=device)
     if world > 1:
@@ -677,6 +690,8 @@ def run_ours(args):
         kernels.append({"name": sname + (" (+ C2/C1 exchange)" if world > 1 else ""),
                         "ms_per_step": select_ms, "alg_bytes_per_step": sel_bytes, "hbm_GBps": sel_bytes / select_ms / 1e6,
                         "frac_hbm": sel_bytes / select_ms / 1e6 / hbm_peak})
+        if chain_ms:        # this rank's split of the chain (CUDA events between its parts)
+            kernels[-1]["parts_ms_rank0"] = {k_: round(v_, 4) for k_, v_ in chain_ms.items()}
     if wl == "hybrid" and split:
         # bytes_hybrid(B) = N d 4 + B (8 P + 8 N) + B 8 N   (one corpus pass whatever B)
         step_bytes = n_shard * shard.ld * 4 + kernels[1]["alg_bytes_per_step"] + 8 * n_shard * B
@@ -748,7 +763,7 @@ def run_ours(args):
     if wl == "hybrid" and world == 1 and not args.no_extras:
         pts = []
         # SURVEY 8(d) north-star points B in {1, 32, 256} (+ 8, the largest batch of ONE pass of the CUDA-core fp32 scan)
-        for pb, mode in ((1, "fp32"), (8, "fp32"), (32, "bf16_exact"), (128, "tf32x3"), (256, "bf16_exact")):
+        for pb, mode in ((1, "fp32"), (8, "fp32"), (32, "bf16_exact"), (128, "bf16_exact"), (128, "tf32x3"), (256, "bf16_exact")):
             if pb == B and mode == args.dense_mode:
                 continue
             e2 = SearchEngine(shard, max_batch=min(pb, 128 if mode == "tf32x3" else 256), dense_mode=mode)

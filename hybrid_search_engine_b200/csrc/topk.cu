@@ -665,19 +665,22 @@ __global__ void __launch_bounds__(kThreads) verify_stats_kernel(const VerifyPara
     }
 }
 
-template <int KP>
-__global__ void __launch_bounds__(kThreads) verify_topk_kernel(const VerifyParams vp, const FuseParams p,
-                                                               const uint64_t* __restrict__ approx, int k_sel, int k_out,
-                                                               float eps, uint64_t* __restrict__ out,
-                                                               int32_t* __restrict__ flags) {
+// VT threads: the re-scoring is one warp per candidate and latency-bound (a 1.5 KB row + a float64 reduction each), so the
+// lists of <= 512 keys run 32 warps per query; threads >= kThreads fall through the sort loops (n / 2 <= kThreads there).
+template <int KP, int VT>
+__global__ void __launch_bounds__(VT) verify_topk_kernel(const VerifyParams vp, const FuseParams p,
+                                                         const uint64_t* __restrict__ approx, int k_sel, int k_out,
+                                                         float eps, uint64_t* __restrict__ out,
+                                                         int32_t* __restrict__ flags) {
+    static_assert(VT == kThreads || KP / 2 <= kThreads, "bitonic_sort_desc_n strides by kThreads");
     __shared__ uint64_t keys[KP];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const FuseConsts c = load_consts(p, b);
     const float* q = vp.q + (int64_t)b * vp.ld_q;
     const float qn = hs_exact_norm_warp(q, vp.dim, lane);
-    for (int i = tid; i < KP; i += kThreads) keys[i] = 0;
+    for (int i = tid; i < KP; i += VT) keys[i] = 0;
     __syncthreads();
-    for (int i = warp; i < k_sel; i += kThreads / 32) {
+    for (int i = warp; i < k_sel; i += VT / 32) {
         const uint64_t key = approx[(int64_t)b * k_sel + i];
         if (key == 0) continue;                                                    // warp-uniform
         const uint32_t gid = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu);
@@ -690,7 +693,7 @@ __global__ void __launch_bounds__(kThreads) verify_topk_kernel(const VerifyParam
     }
     __syncthreads();
     bitonic_sort_desc_n(keys, KP);
-    for (int i = tid; i < k_out; i += kThreads) out[(int64_t)b * k_out + i] = keys[i];
+    for (int i = tid; i < k_out; i += VT) out[(int64_t)b * k_out + i] = keys[i];
     if (tid == 0) {
         // soundness: every doc outside the approximate list scores at most (its last key) + delta exactly
         const uint64_t last = approx[(int64_t)b * k_sel + k_sel - 1];
@@ -706,13 +709,14 @@ __global__ void __launch_bounds__(kThreads) verify_topk_kernel(const VerifyParam
 
 // CTAs (= candidate lists of k keys) per query.  Every list costs k keys of output, a sort and a slot in the merge,
 // whatever its doc range: on a small shard with a large k (doc-sharded runs, the 256 / 512-key lists of the verified
-// mode) 296 lists of a few thousand docs made the select chain a FIXED cost.  So: at least 64 k docs per list, but
-// enough CTAs over the batch to fill the GPU twice, at most 296, at least 4096 docs each.
+// mode) 296 lists of a few thousand docs made the select chain a FIXED cost.  So: at least 128 k docs per list (at 64 k
+// a 5 M-doc shard ran the 256-key select at 0.62 of HBM against 0.80 for the 10 M one), but enough CTAs over the batch
+// to fill the GPU twice, at most 296, at least 4096 docs each.
 int n_chunks_for(int64_t n, int B, int k) {
     int64_t cap = (n + kChunkDocs - 1) / kChunkDocs;
     if (cap > kMaxChunks) cap = kMaxChunks;
     if (cap < 1) cap = 1;
-    int64_t c = n / ((int64_t)64 * (k > 0 ? k : 1));
+    int64_t c = n / ((int64_t)128 * (k > 0 ? k : 1));
     const int64_t fill = (2 * kMaxChunks + (B > 0 ? B : 1) - 1) / (B > 0 ? B : 1);
     if (c < fill) c = fill;
     if (c > cap) c = cap;
@@ -923,13 +927,14 @@ int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t
     p.wa64 = w_a;
     cudaStream_t st = (cudaStream_t)stream;
     if (k_sel <= 128)
-        verify_topk_kernel<128><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+        verify_topk_kernel<128, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
     else if (k_sel <= 256)
-        verify_topk_kernel<256><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+        verify_topk_kernel<256, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
     else if (k_sel <= 512)
-        verify_topk_kernel<512><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+        verify_topk_kernel<512, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
     else
-        verify_topk_kernel<2048><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+        verify_topk_kernel<2048, kThreads><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys,
+                                                                   flags);
     HS_LAUNCH_CHECK();
     return HS_OK;
 }

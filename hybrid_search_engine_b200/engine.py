@@ -325,24 +325,37 @@ class SearchEngine:
         pending = deque()
 
         def collect(item):
-            ev, hs, hi = item
+            ev, hs, hi, hf, qb = item
             ev.synchronize()
-            return hs.numpy().copy(), hi.numpy().copy()
+            sc, ids = hs.numpy().copy(), hi.numpy().copy()
+            if hf is not None:
+                # bf16_exact: the verification flags travel with the result, so the loop never waits for the GPU between
+                # batches; a flagged query (rare) is redone in the exact mode here, before its batch is handed over
+                bad = np.nonzero(hf.numpy()[:len(qb)])[0].tolist()
+                if bad:
+                    s2, i2 = self._redo_exact(qb, bad, k, HS_FUSE_HYBRID_BM25, ws, wl, True, True)
+                    sc[bad], ids[bad] = s2.cpu().numpy(), i2.cpu().numpy()
+            return sc, ids
 
         try:
             for n, qb in enumerate(batches):
                 if len(pending) == depth:          # the slot reused below must have been drained
                     yield collect(pending.popleft())
                 self._pin_slot = n % depth
-                sc, ids = self.search_hybrid_bm25(qb, k, ws, wl, dense_mode)
+                deferred = []
+                sc, ids = self._run(qb, k, HS_FUSE_HYBRID_BM25, ws, wl, True, True, dense_mode, deferred_flags=deferred)
                 with torch.cuda.device(self.device):
                     hs = self._pinned("out_s", tuple(sc.shape), sc.dtype)
                     hi = self._pinned("out_i", tuple(ids.shape), ids.dtype)
                     hs.copy_(sc, non_blocking=True)
                     hi.copy_(ids, non_blocking=True)
+                    hf = None
+                    if deferred:
+                        hf = self._pinned("out_f", tuple(deferred[0].shape), deferred[0].dtype)
+                        hf.copy_(deferred[0], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record()
-                pending.append((ev, hs, hi))
+                pending.append((ev, hs, hi, hf, qb))
             while pending:
                 yield collect(pending.popleft())
         finally:
@@ -483,11 +496,14 @@ class SearchEngine:
         st = stream_ptr(self.device)
         marks = self.phase_events          # bench.py: a list -> one CUDA event per phase boundary of every sub-batch
 
-        def mark():
+        def mark(name=None):
             if marks is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
-                marks.append(ev)
+                if name is None:
+                    marks.append(ev)
+                else:                      # finer marks inside the last phase: (name of the part that just ended, event)
+                    marks.extra.append((name, ev)) if hasattr(marks, "extra") else None
         mark()
         n_seg = self.lib.hs_dense_gemm_filter_segments(self.shard.handle, m)
         cap = self.VERIFY_EXT_CAP
@@ -503,22 +519,38 @@ class SearchEngine:
         mark()
         check(self.lib.hs_verify_stats(self.shard.handle, ptr(qd), nb, qd.stride(0), ptr(ext), ptr(ext_cnt), n_seg, cap,
                                        float(eps), ptr(stats), ptr(flags), st), "hs_verify_stats")
+        mark("verify_stats")
         stats = self._exchange_stats(stats, nb)
+        mark("exchange_stats")
         # candidates re-scored per query: the smaller the list the cheaper the select, but the k-th exact score must clear
         # the bound on the docs outside it (else the query falls back): 2.56 k by default, widened for good once more than
         # 5 % of a call's queries fell back (see _run)
         k_sel = (256 if k <= 100 and not self.verify_wide else 512) if k <= 256 else HS_TOPK_MAX
         approx = self.fuse_topk(mode, cos, b, stats, wa, wb, k_sel, merge=False, out="vkeys")
+        mark("select")
         keys = self._buf("keys", (nb, k), torch.int64)
         check(self.lib.hs_verify_topk(self.shard.handle, ptr(qd), nb, qd.stride(0), mode, ptr(b), ptr(stats), float(wa),
                                       float(wb), ptr(approx), k_sel, k, float(eps), ptr(keys), ptr(flags), st),
               "hs_verify_topk")
         self.launches += 2 * self._gemm_passes(nb, m) + 3
+        mark("verify_topk")
         keys = self._merge_across(keys)
         mark()
         return keys
 
-    def _run(self, qb, k, mode, wa, wb, use_dense, use_bm25, dense_mode, lex=None, plus_delta=None):
+    def _redo_exact(self, qb, bad, k, mode, wa, wb, use_dense, use_bm25, lex=None, plus_delta=None):
+        """The queries ``bad`` of ``qb`` again, in the exact mode (every rank calls this with the same list)."""
+        self.verify_fallbacks = getattr(self, "verify_fallbacks", 0) + len(bad)
+        if len(bad) > max(1, len(qb) // 20):
+            self.verify_wide = True
+        sub = QueryBatch(vectors=None if qb.vectors is None else qb.vectors[bad],
+                         term_ids=None if qb.term_ids is None else [qb.term_ids[i] for i in bad])
+        lx = None if lex is None else lex[bad]
+        return self._run(sub, k, mode, wa, wb, use_dense, use_bm25, "exact", lex=lx, plus_delta=plus_delta)
+
+    def _run(self, qb, k, mode, wa, wb, use_dense, use_bm25, dense_mode, lex=None, plus_delta=None, deferred_flags=None):
+        """``deferred_flags`` (a list): in the verified mode, do not read the verification flags back here -- append the
+        device tensor (already reduced over the shards) and leave the exact redo of flagged queries to the caller."""
         B = len(qb)
         out_s, out_i = [], []
         verify = use_dense and (dense_mode or self.dense_mode) == "bf16_exact"
@@ -571,16 +603,13 @@ class SearchEngine:
             if self.group is not None and self.world > 1:
                 from .parallel import all_reduce_
                 all_reduce_(flags, "max", self.group)
+            if deferred_flags is not None:
+                deferred_flags.append(flags)
+                return sc, ids
             bad = torch.nonzero(flags[:B]).flatten().cpu().tolist()
-            self.verify_fallbacks = getattr(self, "verify_fallbacks", 0) + len(bad)
-            if len(bad) > max(1, B // 20):
-                self.verify_wide = True
             if bad:
                 sc, ids = sc.clone(), ids.clone()
-                sub = QueryBatch(vectors=None if qb.vectors is None else qb.vectors[bad],
-                                 term_ids=None if qb.term_ids is None else [qb.term_ids[i] for i in bad])
-                lx = None if lex is None else lex[bad]
-                s2, i2 = self._run(sub, k, mode, wa, wb, use_dense, use_bm25, "exact", lex=lx, plus_delta=plus_delta)
+                s2, i2 = self._redo_exact(qb, bad, k, mode, wa, wb, use_dense, use_bm25, lex=lex, plus_delta=plus_delta)
                 idx = torch.tensor(bad, dtype=torch.int64, device=self.device)
                 sc[idx], ids[idx] = s2, i2
         return sc, ids

@@ -221,3 +221,39 @@ def test_bf16_exact_pipeline_matches_oracle_on_real_text(hs):
         ids, sc, _ = orc.search_hybrid_bm25(ix, q, c.q_emb[qi], 50)
         assert [r["doc_id"] for r in res[qi].results] == ids.tolist(), q
         assert np.array_equal(np.array([r["score"] for r in res[qi].results], np.float32), sc), q
+
+
+def test_bf16_exact_falls_back_when_the_bound_cannot_be_proven(hs):
+    """A corpus of near-duplicate vectors: every cosine lies inside the bf16 error band, so no top-k can be PROVEN from
+    the screen -- every query must be flagged and redone in the exact mode, in the one-shot call and in the serving
+    loop (where the flags are read back with the result, not between batches).  Result == exact mode, bit for bit."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=60_000, vocab=20_000, dim=96)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, torch.device("cuda:0"))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.randn(spec.dim, device="cuda", generator=g)
+    v = base[None, :] + 1e-4 * torch.randn((spec.n_docs, spec.dim), device="cuda", generator=g)
+    shard.set_dense(v.contiguous())
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    sizes = [20, 7, 20]
+    batches, o = [], 0
+    for B in sizes:
+        batches.append(QueryBatch(vectors=synth.query_embeddings(spec, o, o + B),
+                                  term_ids=synth.query_terms(spec, o, o + B, th).tolist()))
+        o += B
+    eng = SearchEngine(shard, max_batch=32)
+    want = []
+    for qb in batches:
+        sc, ids = eng.search_hybrid_bm25(qb, 50, 0.6, 0.4, dense_mode="exact")
+        want.append((sc.cpu().numpy().copy(), ids.cpu().numpy().copy()))
+    eng.verify_fallbacks = 0
+    for qb, (ws_, wi) in zip(batches, want):
+        sc, ids = eng.search_hybrid_bm25(qb, 50, 0.6, 0.4, dense_mode="bf16_exact")
+        assert np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(sc.cpu().numpy(), ws_)
+    assert eng.verify_fallbacks >= sum(sizes) // 2, eng.verify_fallbacks
+    eng.verify_fallbacks = 0
+    got = list(eng.search_hybrid_bm25_stream(batches, 50, 0.6, 0.4, dense_mode="bf16_exact"))
+    assert eng.verify_fallbacks >= sum(sizes) // 2, eng.verify_fallbacks
+    for (gs, gi), (ws_, wi) in zip(got, want):
+        assert np.array_equal(gi, wi) and np.array_equal(gs, ws_)
