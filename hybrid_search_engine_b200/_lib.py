@@ -23,6 +23,9 @@ DENSE_MODES = {"exact": HS_DENSE_EXACT, "fp32": HS_DENSE_FP32, "bf16": HS_DENSE_
 # |sum q~v~ - sum qv| <= (2^-8 + 2^-18) sum|q_i v_i| <= 2^-8 |q||v| (Cauchy-Schwarz); + 2^-13 for the tensor core's
 # truncating float32 accumulation (measured 2^-20) and the float32 scaling by the norms
 VERIFY_EPS = {"bf16_exact": 2.0 ** -8 * 1.001 + 2.0 ** -13 + 2.0 ** -20}
+# the screen scores are STORED as binary16 (half the bytes of the GEMM's write and the select's read): |score| < 2, so the
+# stored value is within 2^-11 of the float32 accumulator -- added to the eps of everything that reads the stored screen
+SCREEN_F16_EPS = 2.0 ** -11
 
 _vp, _i32, _i64, _u32, _u64, _f64, _sz = (C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64,
                                           C.c_double, C.c_size_t)
@@ -54,6 +57,7 @@ SIGNATURES = {
     "hs_keys_kth_score": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "hs_dense_gemm_filter_segments": (_i32, [_vp, _i32]),
     "hs_dense_gemm_ext": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i64, _vp, _sz, _vp, _i64, _vp, _vp, _vp, _i32, _f64, _vp]),
+    "hs_dense_gemm_ext_f16": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _i64, _i64, _vp, _sz, _vp, _i64, _vp, _vp, _vp, _i32, _f64, _vp]),
     "hs_verify_stats": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _f64, _vp, _vp, _vp]),
     "hs_verify_topk": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _f64, _f64, _vp, _i32, _i32, _f64, _vp, _vp, _vp]),
     "hs_cand_select": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _f64, _i32, _i32, _i32, _vp, _vp, _vp]),
@@ -64,6 +68,7 @@ SIGNATURES = {
     "hs_bm25plus_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _f64, _vp, _vp]),
     "hs_fuse_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "hs_fuse_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),
+    "hs_fuse_topk_f16": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _f64, _f64, _i32, _i32, _vp, _sz, _vp, _vp]),
     "hs_topk_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "hs_scatter_keys": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _vp, _vp]),
     "hs_keys_unpack": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),

@@ -30,6 +30,7 @@
 // Rooflines: 2 * B * n * K flop (x3 for tf32x3) against the measured tensor peak; n * K * sizeof(elem) bytes
 // per corpus pass (+ B * n * 4 written by STORE) against HBM.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 
@@ -151,8 +152,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 struct GemmParams {
-    // STORE epilogue: cos[(b0 + q) * cos_ld + (doc - d0)]
+    // STORE epilogue: cos[(b0 + q) * cos_ld + (doc - d0)], float32 -- or binary16 (cos_h, cos == nullptr; cos_ld even)
     float* cos;
+    __half* cos_h;
     int64_t cos_ld;
     uint32_t* stats;       // [B, 4] or null
     const float* vnorm;    // [n]
@@ -391,7 +393,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             const int buf = (int)(tile_i & 1);
             const int64_t doc0 = p.d0 + t * kTileN;
             float* inv_vn_tile = s_inv_vn + (grp * 2 + (int)(seq & 1)) * kTileN;   // double-buffered: a warp may
-            {   // 1 / |v_i| of this tile -> smem (zero row -> 0.0, utils.py:49-50)     run one tile ahead of its group
+            if constexpr (KIND != kKindBf16) {                                      // run one tile ahead of its group
+                // 1 / |v_i| of this tile -> smem (zero row -> 0.0, utils.py:49-50).  Not for bf16: its operands are unit
+                // vectors, the accumulator is the cosine.
                 const int64_t d = doc0 + etid;
                 float iv = 0.f;
                 if (d < p.d1) {
@@ -399,9 +403,9 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                     iv = vn != 0.f ? 1.0f / vn : 0.f;
                 }
                 inv_vn_tile[etid] = iv;
+                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the four warps of this group only
+                else asm volatile("bar.sync 2, 128;" ::: "memory");
             }
-            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the four warps of this group only
-            else asm volatile("bar.sync 2, 128;" ::: "memory");
             mbar_wait(&tmem_full[buf], (uint32_t)((tile_i >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ndoc = (int)((p.d1 - doc0 < kTileN) ? (p.d1 - doc0) : kTileN);
@@ -443,7 +447,10 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                     // made the compiler keep every later load behind it (possible aliasing through generic pointers), which
                     // serialised 256 shared-memory round trips per tile and starved the tensor pipe (12 % active).
                     float v[32];
-                    {
+                    if constexpr (KIND == kKindBf16) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    } else {
                         const float4* ivp = reinterpret_cast<const float4*>(inv_vn_tile + c0);
                         const float qn = inv_qn[mt];
 #pragma unroll
@@ -510,7 +517,24 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
 #pragma unroll
                         for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
                         __syncwarp();
-                        if (c0 + lane < ndoc) {
+                        if (p.cos_h != nullptr) {
+                            // binary16 screen scores: two query rows per instruction, one __half2 (two docs) per lane -- 16
+                            // stores of 2 x 64 contiguous bytes per chunk; the padded tile keeps both reads conflict-free.
+                            // (Storing straight from the registers -- 16 bytes per ROW and instruction, no transpose -- was
+                            // measured: 3.7x slower, every store instruction touches 32 different lines.)
+                            const int sub = lane & 15, rsel = lane >> 4, dcol = c0 + 2 * sub;
+                            __half* dst = p.cos_h + (int64_t)(p.b0 + mt * kTileM + e * 32 + rsel) * p.cos_ld + (doc0 - p.d0) + dcol;
+#pragma unroll
+                            for (int q = 0; q < 32; q += 2) {
+                                if (q + rsel < nrow) {
+                                    const float x0 = tr[(q + rsel) * 33 + 2 * sub], x1 = tr[(q + rsel) * 33 + 2 * sub + 1];
+                                    if (dcol + 1 < ndoc)
+                                        *reinterpret_cast<__half2*>(dst + (int64_t)q * p.cos_ld) = __floats2half2_rn(x0, x1);
+                                    else if (dcol < ndoc)
+                                        dst[(int64_t)q * p.cos_ld] = __float2half_rn(x0);
+                                }
+                            }
+                        } else if (c0 + lane < ndoc) {
                             float* dst = p.cos + (int64_t)(p.b0 + mt * kTileM + e * 32) * p.cos_ld + (doc0 - p.d0) + c0 + lane;
 #pragma unroll
                             for (int q = 0; q < 32; ++q)
@@ -587,9 +611,7 @@ __global__ void gemm_prepare_queries_kernel(const float* __restrict__ q, int64_t
     for (int e = lane; e < kpad; e += 32) {
         float x = 0.f;
         if (b < nq_valid && e < dim) x = q[(int64_t)(b0 + b) * ld_q + e];
-        if constexpr (KIND == kKindBf16) {
-            reinterpret_cast<__nv_bfloat16*>(out_hi)[(int64_t)b * kpad + e] = __float2bfloat16_rn(x);
-        } else {
+        if constexpr (KIND != kKindBf16) {
             reinterpret_cast<float*>(out_hi)[(int64_t)b * kpad + e] = x;
             out_lo[(int64_t)b * kpad + e] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
         }
@@ -597,10 +619,18 @@ __global__ void gemm_prepare_queries_kernel(const float* __restrict__ q, int64_t
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) qq += hs_shfl_xor_f64(qq, m);
-    if (lane == 0) {
-        const float qn = (float)sqrt(qq);
-        inv_qn[b] = (b < nq_valid && qn != 0.f) ? 1.0f / qn : 0.f;   // zero query -> zeros (utils.py:44-45)
+    const float qn = (float)sqrt(qq);
+    const float inv = (b < nq_valid && qn != 0.f) ? 1.0f / qn : 0.f;   // zero query -> zeros (utils.py:44-45)
+    if constexpr (KIND == kKindBf16) {
+        // bf16: BOTH operands are unit vectors (the corpus rows are normalised when the bf16 matrix is built), so the
+        // accumulator IS the cosine and the epilogue has no scaling to do
+        for (int e = lane; e < kpad; e += 32) {
+            float x = 0.f;
+            if (b < nq_valid && e < dim) x = q[(int64_t)(b0 + b) * ld_q + e];
+            reinterpret_cast<__nv_bfloat16*>(out_hi)[(int64_t)b * kpad + e] = __float2bfloat16_rn(x * inv);
+        }
     }
+    if (lane == 0) inv_qn[b] = inv;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -661,6 +691,8 @@ bool make_plan(int kind, int mt, int epi, int64_t ld_elems, Plan& pl) {
     const int stage = pl.q_resident ? v_bytes : v_bytes + q_blk;
     int64_t stages = (avail - (pl.q_resident ? q_all : 0)) / stage;
     if (stages > kMaxStages) stages = kMaxStages;
+    static const int cap = getenv("HS_GEMM_MAX_STAGES") ? atoi(getenv("HS_GEMM_MAX_STAGES")) : 0;   // experiment switch
+    if (cap >= 2 && stages > cap) stages = cap;
     pl.stages = (int)stages;
     pl.smem = 1024 + (size_t)(pl.q_resident ? q_all : 0) + (size_t)pl.stages * stage + kSmemMisc + tr;
     return stages >= 2;
@@ -733,7 +765,8 @@ int pick_cluster(int kind, int mt, const Plan& pl, int64_t n_tiles, int num_sms)
 int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t d0, int64_t d1,
              void* workspace, size_t workspace_bytes, int epi, float* cos, int64_t cos_ld, const float* thr,
              uint64_t* cand, int32_t seg_cap, uint32_t* cand_cnt, uint32_t* stats_enc, void* stream, const char* who,
-             uint64_t* ext = nullptr, uint32_t* ext_cnt = nullptr, int32_t ext_cap = 0, float eps2 = 0.f) {
+             uint64_t* ext = nullptr, uint32_t* ext_cnt = nullptr, int32_t ext_cap = 0, float eps2 = 0.f,
+             uint16_t* cos_h = nullptr) {
     HS_REQUIRE(idx != nullptr, "%s: idx is null", who);
     HS_REQUIRE(mode == HS_DENSE_BF16 || mode == HS_DENSE_TF32X3, "%s: mode %d is not a tensor-core mode", who, mode);
     HS_REQUIRE(d0 >= 0 && d0 <= d1 && d1 <= idx->n_docs, "%s: doc range [%lld, %lld) outside the shard", who,
@@ -782,6 +815,7 @@ int gemm_run(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q,
         }
         GemmParams p;
         p.cos = cos;
+        p.cos_h = (__half*)cos_h;
         p.cos_ld = cos_ld;
         p.stats = stats_enc;
         p.vnorm = idx->vnorm;
@@ -865,6 +899,18 @@ int hs_dense_gemm_ext(const hs_index* idx, const float* queries, int32_t B, int6
     return gemm_run(idx, queries, B, ld_q, mode, doc_lo, doc_hi, workspace, workspace_bytes, kEpiStore, cos, cos_ld,
                     nullptr, nullptr, 0, nullptr, stats_enc, stream, "hs_dense_gemm_ext", ext, ext_cnt, ext_cap,
                     (float)(2.0 * eps));
+}
+
+int hs_dense_gemm_ext_f16(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t doc_lo,
+                          int64_t doc_hi, void* workspace, size_t workspace_bytes, uint16_t* cos_f16, int64_t cos_ld,
+                          uint32_t* stats_enc, uint64_t* ext, uint32_t* ext_cnt, int32_t ext_cap, double eps, void* stream) {
+    HS_REQUIRE(cos_f16 != nullptr && cos_ld >= doc_hi - doc_lo && (cos_ld & 7) == 0 && ((uintptr_t)cos_f16 & 15) == 0,
+               "hs_dense_gemm_ext_f16: cos_f16 is null / misaligned, or cos_ld < doc range or not a multiple of 8");
+    HS_REQUIRE(ext != nullptr && ext_cnt != nullptr && ext_cap > 0 && eps >= 0.0 && stats_enc != nullptr,
+               "hs_dense_gemm_ext_f16: bad extreme-candidate buffers");
+    return gemm_run(idx, queries, B, ld_q, mode, doc_lo, doc_hi, workspace, workspace_bytes, kEpiStore, nullptr, cos_ld,
+                    nullptr, nullptr, 0, nullptr, stats_enc, stream, "hs_dense_gemm_ext_f16", ext, ext_cnt, ext_cap,
+                    (float)(2.0 * eps), cos_f16);
 }
 
 int32_t hs_dense_gemm_filter_segments(const hs_index* idx, int32_t mode) {

@@ -22,6 +22,8 @@
 
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 namespace {
@@ -163,6 +165,7 @@ struct Selector {
 
 struct FuseParams {
     const float* a;
+    const __half* a16;    // the a array as IEEE binary16 (the verified mode's SCREEN scores) when a == nullptr
     const float* b;
     const uint32_t* stats;
     const uint64_t* below;
@@ -170,11 +173,38 @@ struct FuseParams {
     unsigned long long* gthr;   // [B] published lower bounds on the k-th best key (zeroed per call)
     uint64_t* blockmax;         // [B, kBoundBlocks] best key of each sampled block (workspace)
     int64_t n, doc_base;
-    int64_t ld;                 // row stride of a and b (elements)
+    int64_t ld;                 // row stride of b (elements)
+    int64_t ld_a;               // row stride of a / a16 (elements)
     int mode, k, n_chunks;
     int n_bound;                // blocks sampled for the starting bound (0 = none)
     float wa32, wb32;
     double wa64;
+};
+
+// One row of the a array: float32, or binary16 for the screen scores of the verified mode (half the bytes of the
+// GEMM's write and of this pass's read; the rounding is covered by the verification's eps).
+template <bool AH>
+struct ARow;
+template <>
+struct ARow<false> {
+    const float* p;
+    __device__ __forceinline__ ARow(const FuseParams& fp, int b) : p(fp.a + (int64_t)b * fp.ld_a) {}
+    __device__ __forceinline__ float at(int64_t i) const { return __ldg(p + i); }
+    __device__ __forceinline__ float4 at4(int64_t i) const { return __ldg(reinterpret_cast<const float4*>(p + i)); }
+    __device__ __forceinline__ bool aligned(int64_t i) const { return (reinterpret_cast<uintptr_t>(p + i) & 15) == 0; }
+};
+template <>
+struct ARow<true> {
+    const __half* p;
+    __device__ __forceinline__ ARow(const FuseParams& fp, int b) : p(fp.a16 + (int64_t)b * fp.ld_a) {}
+    __device__ __forceinline__ float at(int64_t i) const { return __half2float(__ldg(p + i)); }
+    __device__ __forceinline__ float4 at4(int64_t i) const {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + i));
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    __device__ __forceinline__ bool aligned(int64_t i) const { return (reinterpret_cast<uintptr_t>(p + i) & 7) == 0; }
 };
 
 struct FuseConsts {
@@ -263,6 +293,7 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
     return v;
 }
 
+template <bool AH>
 __global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParams p) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int blk = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -271,13 +302,13 @@ __global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParam
     const int64_t start = (int64_t)blk * stride;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
-    const float* pa = p.a + (int64_t)b * p.ld;
+    const ARow<AH> pa(p, b);
     const float* pb = p.b ? p.b + (int64_t)b * p.ld : nullptr;
     uint64_t best = 0;
 #pragma unroll
     for (int u = 0; u < kBoundDocs / 32; ++u) {
         const int64_t i = start + u * 32 + lane;
-        const float a = __ldg(pa + i);
+        const float a = pa.at(i);
         const float bb = pb ? __ldg(pb + i) : 0.f;
         const uint64_t kk = hs_make_key(fuse_score(p, c, a, bb), (uint32_t)(p.doc_base + i));
         if (kk < below && kk > best) best = kk;
@@ -302,7 +333,7 @@ __global__ void __launch_bounds__(kThreads) fuse_bound_kernel(const FuseParams p
 // any block-wide synchronisation in the loop (loads of consecutive iterations overlap freely); an append
 // that finds the candidate buffer full only raises a flag.  If the flag is up at the end the chunk is
 // redone with the synchronised selector (always correct, used from the start when there is no bound).
-template <int KP>
+template <int KP, bool AH>
 __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p) {
     __shared__ Selector<KP> sel;
     __shared__ int overflow;
@@ -314,7 +345,7 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
     const int64_t hi = (lo + span < p.n) ? lo + span : p.n;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
-    const float* pa = p.a + (int64_t)b * p.ld;
+    const ARow<AH> pa(p, b);
     const float* pb = p.b ? p.b + (int64_t)b * p.ld : nullptr;
     unsigned long long* gthr = p.gthr + b;
     if (tid == 0) overflow = 0;
@@ -361,15 +392,14 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
         };
         constexpr int kV = 2;                                   // 16-byte loads per array, thread and iteration
         constexpr int kStep = kThreads * 4 * kV;                // 2048 docs per iteration
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(pa + lo) & 15) == 0) &&
-                            (pb == nullptr || (reinterpret_cast<uintptr_t>(pb + lo) & 15) == 0);
+        const bool vec_ok = pa.aligned(lo) && (pb == nullptr || (reinterpret_cast<uintptr_t>(pb + lo) & 15) == 0);
         for (int64_t base = lo; base < hi; base += kStep) {
             if (vec_ok && base + kStep <= hi) {                 // block-uniform
                 float4 a4[kV], b4[kV];
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
                     const int64_t i = base + v * (kThreads * 4) + tid * 4;
-                    a4[v] = __ldg(reinterpret_cast<const float4*>(pa + i));
+                    a4[v] = pa.at4(i);
                     b4[v] = pb != nullptr ? __ldg(reinterpret_cast<const float4*>(pb + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 bool cand = false;
@@ -399,7 +429,7 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
             } else {                                            // unaligned rows and the ragged tail
                 for (int64_t i0 = base + tid; i0 < base + kStep; i0 += kThreads) {
                     const bool valid = i0 < hi;
-                    consider(valid ? __ldg(pa + i0) : 0.f, (valid && pb != nullptr) ? __ldg(pb + i0) : 0.f, i0, valid);
+                    consider(valid ? pa.at(i0) : 0.f, (valid && pb != nullptr) ? __ldg(pb + i0) : 0.f, i0, valid);
                 }
             }
         }
@@ -414,7 +444,7 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
 #pragma unroll
             for (int j = 0; j < kItems; ++j) {
                 const int64_t i = base + j * kThreads + tid;
-                av[j] = (i < hi) ? __ldg(pa + i) : 0.f;
+                av[j] = (i < hi) ? pa.at(i) : 0.f;
                 bv[j] = (pb != nullptr && i < hi) ? __ldg(pb + i) : 0.f;
             }
             // score the current bound stands for (bound 0 = nothing known yet -> -inf)
@@ -743,6 +773,23 @@ int merge_dispatch(const uint64_t* keys, int n_lists, int B, int k, int64_t list
     return launch_merge<2048>(keys, n_lists, B, k, list_stride, query_stride, out, st);
 }
 
+template <bool AH>
+static void launch_fuse_select(const FuseParams& p, dim3 grid, int B, int k, cudaStream_t st) {
+    if (p.n_bound > 0) {
+        dim3 bg((unsigned)(p.n_bound / (kThreads / 32)), (unsigned)B);
+        fuse_blockmax_kernel<AH><<<bg, kThreads, 0, st>>>(p);
+        fuse_bound_kernel<<<B, kThreads, 0, st>>>(p);
+    }
+    if (k <= 128)
+        fuse_topk_kernel<128, AH><<<grid, kThreads, 0, st>>>(p);
+    else if (k <= 256)
+        fuse_topk_kernel<256, AH><<<grid, kThreads, 0, st>>>(p);
+    else if (k <= 512)
+        fuse_topk_kernel<512, AH><<<grid, kThreads, 0, st>>>(p);
+    else
+        fuse_topk_kernel<2048, AH><<<grid, kThreads, 0, st>>>(p);
+}
+
 }  // namespace
 
 extern "C" {
@@ -752,8 +799,9 @@ size_t hs_fuse_topk_workspace_bytes(int64_t n_docs, int32_t B, int32_t k) {
     return ((size_t)B * n_chunks_for(n_docs, B, k) * (size_t)k + (size_t)B + (size_t)B * kBoundBlocks) * sizeof(uint64_t);
 }
 
-static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t fuse_mode, const float* a, const float* b,
-                          const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
+// a: float32 [B, ld], or binary16 [B, ld] when a_half
+static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t fuse_mode, const void* a, bool a_half,
+                          const float* b, const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
                           const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
                           cudaStream_t st) {
     HS_REQUIRE(B > 0 && B <= 65535 && k > 0 && k <= HS_TOPK_MAX, "hs_fuse_topk: B=%d k=%d out of range (k <= %d)", B,
@@ -774,7 +822,8 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
     HS_REQUIRE(workspace != nullptr && workspace_bytes >= need, "hs_fuse_topk: workspace too small (%zu < %zu)",
                workspace_bytes, need);
     FuseParams p;
-    p.a = a;
+    p.a = a_half ? nullptr : (const float*)a;
+    p.a16 = a_half ? (const __half*)a : nullptr;
     p.b = b;
     p.stats = stats_enc;
     p.below = below_key;
@@ -783,7 +832,8 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
     p.cand = (uint64_t*)workspace + B + (size_t)B * kBoundBlocks;
     HS_CUDA(cudaMemsetAsync(p.gthr, 0, (size_t)B * sizeof(uint64_t), st));
     p.n = n_docs;
-    p.ld = ld;
+    p.ld = a_half ? n_docs : ld;          // b rows are a shard's [B, n_docs] array whenever a is the binary16 screen
+    p.ld_a = ld;
     p.doc_base = doc_base;
     p.mode = fuse_mode;
     p.k = k;
@@ -801,20 +851,8 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
             p.n_bound = nb;
             break;
         }
-    if (p.n_bound > 0) {
-        dim3 bg((unsigned)(p.n_bound / (kThreads / 32)), (unsigned)B);
-        fuse_blockmax_kernel<<<bg, kThreads, 0, st>>>(p);
-        fuse_bound_kernel<<<B, kThreads, 0, st>>>(p);
-        HS_LAUNCH_CHECK();
-    }
-    if (k <= 128)
-        fuse_topk_kernel<128><<<grid, kThreads, 0, st>>>(p);
-    else if (k <= 256)
-        fuse_topk_kernel<256><<<grid, kThreads, 0, st>>>(p);
-    else if (k <= 512)
-        fuse_topk_kernel<512><<<grid, kThreads, 0, st>>>(p);
-    else
-        fuse_topk_kernel<2048><<<grid, kThreads, 0, st>>>(p);
+    if (a_half) launch_fuse_select<true>(p, grid, B, k, st);
+    else launch_fuse_select<false>(p, grid, B, k, st);
     HS_LAUNCH_CHECK();
     // candidate layout [B, n_chunks, k]: list stride k, query stride n_chunks * k
     return merge_dispatch(p.cand, p.n_chunks, B, k, (int64_t)k, (int64_t)p.n_chunks * k, out_keys, st);
@@ -825,14 +863,23 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
                  const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
                  void* stream) {
     HS_REQUIRE(idx != nullptr, "hs_fuse_topk: idx is null");
-    return fuse_topk_impl(idx->n_docs, idx->doc_base, idx->n_docs, fuse_mode, a, b, stats_enc, w_a, w_b, B, k, below_key,
+    return fuse_topk_impl(idx->n_docs, idx->doc_base, idx->n_docs, fuse_mode, a, false, b, stats_enc, w_a, w_b, B, k,
+                          below_key, workspace, workspace_bytes, out_keys, (cudaStream_t)stream);
+}
+
+int hs_fuse_topk_f16(const hs_index* idx, int32_t fuse_mode, const uint16_t* a_f16, const float* b, int64_t ld,
+                     const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k, void* workspace,
+                     size_t workspace_bytes, uint64_t* out_keys, void* stream) {
+    HS_REQUIRE(idx != nullptr, "hs_fuse_topk_f16: idx is null");
+    HS_REQUIRE(fuse_mode != HS_FUSE_RAW, "hs_fuse_topk_f16: screen scores are only fused (SEARCHER / HYBRID_BM25)");
+    return fuse_topk_impl(idx->n_docs, idx->doc_base, ld, fuse_mode, a_f16, true, b, stats_enc, w_a, w_b, B, k, nullptr,
                           workspace, workspace_bytes, out_keys, (cudaStream_t)stream);
 }
 
 int hs_topk_select(const float* x, int64_t n, int64_t ld, int64_t doc_base, int32_t B, int32_t k, void* workspace,
                    size_t workspace_bytes, uint64_t* out_keys, void* stream) {
     HS_REQUIRE(n >= 0 && doc_base >= 0 && n + doc_base <= 0xFFFFFFFFll, "hs_topk_select: doc ids must fit uint32");
-    return fuse_topk_impl(n, doc_base, ld, HS_FUSE_RAW, x, nullptr, nullptr, 1.0, 0.0, B, k, nullptr, workspace,
+    return fuse_topk_impl(n, doc_base, ld, HS_FUSE_RAW, x, false, nullptr, nullptr, 1.0, 0.0, B, k, nullptr, workspace,
                           workspace_bytes, out_keys, (cudaStream_t)stream);
 }
 

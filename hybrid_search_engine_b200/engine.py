@@ -19,6 +19,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
+import os
+
 import numpy as np
 import torch
 
@@ -57,6 +59,8 @@ class SearchEngine:
         self._pin_events = {}      # (slot, group) -> event recorded after the last H2D copy out of that staging set
         self.phase_events = None   # bench.py sets a list to collect per-phase CUDA events of the verified chain
         self.verify_wide = False   # bf16_exact: re-score 512 instead of 256 candidates per query (set after fallbacks)
+        # bf16_exact: keep the screen scores as binary16 (HS_SCREEN_F32=1 restores the float32 screen, an A/B switch)
+        self.screen_f16 = os.environ.get("HS_SCREEN_F32", "0") in ("", "0")
         self.launches = 0          # kernels launched by this engine (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------ buffers (never on the hot path twice)
@@ -508,12 +512,21 @@ class SearchEngine:
         n_seg = self.lib.hs_dense_gemm_filter_segments(self.shard.handle, m)
         cap = self.VERIFY_EXT_CAP
         wsp, nbytes = self._gemm_ws(nb, m)
-        cos = self._buf("cos", (nb, n), torch.float32)
         ext = self._buf("vext", (nb, n_seg, 2, cap), torch.int64)
         ext_cnt = self._buf("vext_cnt", (nb, n_seg, 2), torch.int32)
         ext_cnt.zero_()
-        check(self.lib.hs_dense_gemm_ext(self.shard.handle, ptr(qd), nb, qd.stride(0), m, 0, n, wsp, nbytes, ptr(cos), n,
-                                         ptr(stats), ptr(ext), ptr(ext_cnt), cap, float(eps), st), "hs_dense_gemm_ext")
+        f16 = self.screen_f16
+        if f16:      # screen scores as binary16 [nb, ld_h]: 2 bytes per (query, doc) written here and re-read by the select
+            ld_h = (n + 7) // 8 * 8
+            cos = self._buf("cos_h", (nb, ld_h), torch.float16)
+            eps = eps + _lib.SCREEN_F16_EPS
+            check(self.lib.hs_dense_gemm_ext_f16(self.shard.handle, ptr(qd), nb, qd.stride(0), m, 0, n, wsp, nbytes, ptr(cos),
+                                                 ld_h, ptr(stats), ptr(ext), ptr(ext_cnt), cap, float(eps), st),
+                  "hs_dense_gemm_ext_f16")
+        else:
+            cos = self._buf("cos", (nb, n), torch.float32)
+            check(self.lib.hs_dense_gemm_ext(self.shard.handle, ptr(qd), nb, qd.stride(0), m, 0, n, wsp, nbytes, ptr(cos), n,
+                                             ptr(stats), ptr(ext), ptr(ext_cnt), cap, float(eps), st), "hs_dense_gemm_ext")
         mark()
         b = bm(stats) if callable(bm) else bm
         mark()
@@ -526,7 +539,15 @@ class SearchEngine:
         # the bound on the docs outside it (else the query falls back): 2.56 k by default, widened for good once more than
         # 5 % of a call's queries fell back (see _run)
         k_sel = (256 if k <= 100 and not self.verify_wide else 512) if k <= 256 else HS_TOPK_MAX
-        approx = self.fuse_topk(mode, cos, b, stats, wa, wb, k_sel, merge=False, out="vkeys")
+        if f16:
+            ws_bytes = self.lib.hs_fuse_topk_workspace_bytes(n, nb, k_sel)
+            ws = self._buf("topk_ws", (max(ws_bytes // 8, 1),), torch.int64)
+            approx = self._buf("vkeys", (nb, k_sel), torch.int64)
+            check(self.lib.hs_fuse_topk_f16(self.shard.handle, mode, ptr(cos), ptr(b), cos.stride(0), ptr(stats), float(wa),
+                                            float(wb), nb, k_sel, ptr(ws), ws_bytes, ptr(approx), st), "hs_fuse_topk_f16")
+            self.launches += 2
+        else:
+            approx = self.fuse_topk(mode, cos, b, stats, wa, wb, k_sel, merge=False, out="vkeys")
         mark("select")
         keys = self._buf("keys", (nb, k), torch.int64)
         check(self.lib.hs_verify_topk(self.shard.handle, ptr(qd), nb, qd.stride(0), mode, ptr(b), ptr(stats), float(wa),

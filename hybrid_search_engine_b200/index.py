@@ -84,6 +84,7 @@ class DeviceIndex:
             vectors = padded
         self.vectors = vectors.contiguous()
         self.dim, self.ld = dim, ld
+        self.vectors_bf16 = None           # a bf16 copy of an earlier matrix is stale now (ensure_bf16 rebuilds it)
         self.vnorm = torch.empty(self.n_docs, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(self.lib.hs_row_norms(ptr(self.vectors), self.n_docs, dim, ld, ptr(self.vnorm),
@@ -92,7 +93,8 @@ class DeviceIndex:
                   "hs_index_set_dense")
 
     def ensure_bf16(self):
-        """bf16 copy of the matrix, rows padded to a multiple of 64 elements (tcgen05 GEMM path)."""
+        """bf16 copy of the matrix with UNIT rows, bf16(v / |v|) (zero rows stay zero), rows padded to a multiple of 64
+        elements: the operand of the tcgen05 GEMM, whose accumulator is then the cosine itself."""
         if getattr(self, "vectors_bf16", None) is not None:
             return
         if self.vectors is None:
@@ -101,7 +103,9 @@ class DeviceIndex:
         v16 = torch.zeros((self.n_docs, ld16), dtype=torch.bfloat16, device=self.device)
         step = 1 << 20
         for s in range(0, self.n_docs, step):                   # chunked: no second float32 copy
-            v16[s:s + step, :self.dim] = self.vectors[s:s + step, :self.dim].to(torch.bfloat16)
+            vn = self.vnorm[s:s + step]
+            inv = torch.where(vn > 0, 1.0 / vn, torch.zeros_like(vn))
+            v16[s:s + step, :self.dim] = (self.vectors[s:s + step, :self.dim] * inv[:, None]).to(torch.bfloat16)
         self.vectors_bf16 = v16
         self.ld_bf16 = ld16
         check(self.lib.hs_index_set_dense_bf16(self.handle, ptr(v16), ld16), "hs_index_set_dense_bf16")

@@ -114,8 +114,10 @@ int hs_dense_scan(const hs_index* idx, const float* queries, int32_t B, int64_t 
 
 /* K2b the same scan at large query batch on the tensor cores (tcgen05 GEMM, one corpus pass serves 128-256
  *     queries) over the doc range [doc_lo, doc_hi) of the shard:
- *       HS_DENSE_BF16    needs a bf16 copy of the matrix, [n_docs, ld_bf16] with ld_bf16 a multiple of 64 (zero
- *                        padded); agrees with the float32 path within 1e-2 (stage-1 retrieval)
+ *       HS_DENSE_BF16    needs a bf16 copy of the matrix with UNIT rows, bf16(v_i / |v_i|) (zero rows stay zero),
+ *                        [n_docs, ld_bf16] with ld_bf16 a multiple of 64 (zero padded); the queries are normalised the
+ *                        same way on the fly, so the accumulator is the cosine itself (no scaling in the epilogue);
+ *                        agrees with the float32 path within 2^-8 (stage-1 retrieval)
  *       HS_DENSE_TF32X3  reads the float32 matrix itself, split hi/lo on the fly: float32-grade accuracy
  *     Norms stay float32.  cos[b, i - doc_lo] float32 with row stride cos_ld; min/max folded into stats. */
 int hs_index_set_dense_bf16(hs_index* idx, const void* v_bf16, int64_t ld_bf16);
@@ -130,6 +132,13 @@ int hs_dense_gemm(const hs_index* idx, const float* queries, int32_t B, int64_t 
 int hs_dense_gemm_ext(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t doc_lo,
                       int64_t doc_hi, void* workspace, size_t workspace_bytes, float* cos, int64_t cos_ld,
                       uint32_t* stats_enc, uint64_t* ext, uint32_t* ext_cnt, int32_t ext_cap, double eps, void* stream);
+/* hs_dense_gemm_ext with the SCREEN scores stored as IEEE binary16 [B, cos_ld] (cos_ld a multiple of 8, base 16-byte
+ * aligned): half the bytes written here and re-read by hs_fuse_topk_f16.  Statistics and extreme lists come from the
+ * float32 accumulators as before; the stored value differs from them by <= 2^-11 (|score| < 2), which the caller adds to
+ * the eps it hands hs_verify_topk. */
+int hs_dense_gemm_ext_f16(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode, int64_t doc_lo,
+                          int64_t doc_hi, void* workspace, size_t workspace_bytes, uint16_t* cos_f16, int64_t cos_ld,
+                          uint32_t* stats_enc, uint64_t* ext, uint32_t* ext_cnt, int32_t ext_cap, double eps, void* stream);
 /* Exact verification of an approximate scan (screen on the tensor cores, verify in the conformance order; no reference
  * counterpart -- it is what lets the bf16 GEMM return the reference's exact ranking):
  *   hs_verify_stats  replaces stats slots MIN_A / MAX_A by the EXACT min / max cosine of the shard (utils.py:67-68),
@@ -197,6 +206,11 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
                  const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
                  const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
                  void* stream);
+/* hs_fuse_topk whose a array is the binary16 screen of hs_dense_gemm_ext_f16 (row stride ld elements; b float32 [B, n_docs]):
+ * the approximate select of the verified mode (fuse_mode SEARCHER or HYBRID_BM25; results go to hs_verify_topk). */
+int hs_fuse_topk_f16(const hs_index* idx, int32_t fuse_mode, const uint16_t* a_f16, const float* b, int64_t ld,
+                     const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k, void* workspace,
+                     size_t workspace_bytes, uint64_t* out_keys, void* stream);
 /* top_k_indices (utils.py:74-87) of a float32 [B, n] array with row stride ld that is not a whole shard (e.g. the
  * sample block of the filtered tensor-core scan): keys carry doc_base + position */
 int hs_topk_select(const float* x, int64_t n, int64_t ld, int64_t doc_base, int32_t B, int32_t k, void* workspace,

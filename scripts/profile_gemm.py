@@ -1,5 +1,5 @@
 """Small fixed workloads for ncu.   python scripts/profile_gemm.py <what> [n_docs] [dim]
-   what: filter_bf16 | filter_tf32 | store_bf16_256 | store_tf32 | hybrid_tf32 | hybrid_bf16x | hybrid_fp32"""
+   what: filter_bf16 | filter_tf32 | store_bf16_256 | store_tf32 | hybrid_tf32 | hybrid_bf16x | hybrid_bf16x256 | hybrid_fp32"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,7 +28,8 @@ elif what.startswith("store"):
     for _ in range(reps):
         eng.dense_scan(qd, stats)
 else:
-    mode, B = {"hybrid_tf32": ("tf32x3", 128), "hybrid_bf16x": ("bf16_exact", 128)}.get(what, ("fp32", 8))
+    mode, B = {"hybrid_tf32": ("tf32x3", 128), "hybrid_bf16x": ("bf16_exact", 128),
+               "hybrid_bf16x256": ("bf16_exact", 256)}.get(what, ("fp32", 8))
     eng = SearchEngine(shard, max_batch=B, dense_mode=mode)
     qb = QueryBatch(vectors=synth.query_embeddings(spec, 0, B), term_ids=synth.query_terms(spec, 0, B, th).tolist())
     for _ in range(reps):

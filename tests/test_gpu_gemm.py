@@ -207,6 +207,29 @@ def test_bf16_exact_mode_is_bit_identical_to_exact(hs, B, k):
     want = [t.cpu().numpy().copy() for t in eng.search_searcher(qs, lex, k, 0.7, 0.3, dense_mode="exact")]
     assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
     print(f"bf16_exact: {getattr(eng, 'verify_fallbacks', 0)} of {2 * B + lex.shape[0]} queries fell back to the exact mode")
+    # the float32 screen (HS_SCREEN_F32=1; the default keeps the screen scores as binary16) proves the same result
+    eng.max_batch, eng.screen_f16 = 256, False
+    got = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="bf16_exact")]
+    eng.max_batch = 8
+    want = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="exact")]
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+
+
+@pytest.mark.parametrize("n_docs", [50_003, 4_099, 130])
+def test_bf16_exact_ragged_shard_sizes(hs, n_docs):
+    """Shard sizes that are not a multiple of 2 / 8 / 128: the binary16 screen rows are padded to 8 elements, the last
+    tile stores a lone half, the select's vector path falls back on the ragged tail -- still the exact mode's bits."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=n_docs, vocab=5_000, dim=72)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, torch.device("cuda:0"))
+    th = synth.zipf_thresholds(spec.vocab, spec.zipf_s)
+    B, k = 37, 20
+    qb = QueryBatch(vectors=synth.query_embeddings(spec, 0, B), term_ids=synth.query_terms(spec, 0, B, th).tolist())
+    eng = SearchEngine(shard, max_batch=64)
+    got = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="bf16_exact")]
+    want = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="exact")]
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
 
 
 def test_bf16_exact_pipeline_matches_oracle_on_real_text(hs):
