@@ -512,33 +512,42 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                                 }
                             }
                         }
-                        // transpose through smem so that the global stores run along the docs of ONE query (128 contiguous
-                        // bytes per instruction)
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
-                        __syncwarp();
+                        // transpose through smem so that the global stores run along the docs of ONE query
                         if (p.cos_h != nullptr) {
-                            // binary16 screen scores: two query rows per instruction, one __half2 (two docs) per lane -- 16
-                            // stores of 2 x 64 contiguous bytes per chunk; the padded tile keeps both reads conflict-free.
+                            // binary16 screen scores, packed BEFORE the transpose: 16 half2 words per query row (row stride 17
+                            // words: conflict-free writes); store instruction i covers rows i and i + 16 (272 words apart =
+                            // the other half of the banks), one half2 = two docs per lane -> 2 x 64 contiguous bytes.
                             // (Storing straight from the registers -- 16 bytes per ROW and instruction, no transpose -- was
                             // measured: 3.7x slower, every store instruction touches 32 different lines.)
-                            const int sub = lane & 15, rsel = lane >> 4, dcol = c0 + 2 * sub;
-                            __half* dst = p.cos_h + (int64_t)(p.b0 + mt * kTileM + e * 32 + rsel) * p.cos_ld + (doc0 - p.d0) + dcol;
+                            uint32_t* trh = reinterpret_cast<uint32_t*>(tr);
 #pragma unroll
-                            for (int q = 0; q < 32; q += 2) {
-                                if (q + rsel < nrow) {
-                                    const float x0 = tr[(q + rsel) * 33 + 2 * sub], x1 = tr[(q + rsel) * 33 + 2 * sub + 1];
+                            for (int w = 0; w < 16; ++w) {
+                                const __half2 h = __floats2half2_rn(v[2 * w], v[2 * w + 1]);
+                                trh[lane * 17 + w] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            __syncwarp();
+                            const int sub = lane & 15, rsel = lane >> 4, dcol = c0 + 2 * sub;
+                            __half* dst = p.cos_h + (int64_t)(p.b0 + mt * kTileM + e * 32 + 16 * rsel) * p.cos_ld + (doc0 - p.d0) + dcol;
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) {
+                                if (q + 16 * rsel < nrow) {
+                                    const uint32_t w = trh[(q + 16 * rsel) * 17 + sub];
                                     if (dcol + 1 < ndoc)
-                                        *reinterpret_cast<__half2*>(dst + (int64_t)q * p.cos_ld) = __floats2half2_rn(x0, x1);
+                                        *reinterpret_cast<uint32_t*>(dst + (int64_t)q * p.cos_ld) = w;
                                     else if (dcol < ndoc)
-                                        dst[(int64_t)q * p.cos_ld] = __float2half_rn(x0);
+                                        dst[(int64_t)q * p.cos_ld] = __ushort_as_half((unsigned short)(w & 0xFFFFu));
                                 }
                             }
-                        } else if (c0 + lane < ndoc) {
-                            float* dst = p.cos + (int64_t)(p.b0 + mt * kTileM + e * 32) * p.cos_ld + (doc0 - p.d0) + c0 + lane;
+                        } else {
 #pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (q < nrow) dst[(int64_t)q * p.cos_ld] = tr[q * 33 + lane];
+                            for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+                            __syncwarp();
+                            if (c0 + lane < ndoc) {
+                                float* dst = p.cos + (int64_t)(p.b0 + mt * kTileM + e * 32) * p.cos_ld + (doc0 - p.d0) + c0 + lane;
+#pragma unroll
+                                for (int q = 0; q < 32; ++q)
+                                    if (q < nrow) dst[(int64_t)q * p.cos_ld] = tr[q * 33 + lane];
+                            }
                         }
                         __syncwarp();
                     } else {
