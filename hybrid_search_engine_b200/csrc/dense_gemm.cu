@@ -38,7 +38,8 @@
 
 namespace {
 
-constexpr int kThreads = 384;         // TMA warp, MMA warp, 2 idle, 8 epilogue / converter warps
+// TMA warp, MMA warp, 2 idle, then bf16: 16 epilogue warps (4 groups); tf32x3: 4 epilogue + 4 converter warps
+constexpr int threads_of(int kind) { return kind == 0 ? 640 : 384; }
 constexpr int kTileN = 128;           // docs per tile = UMMA N = TMEM columns per accumulator
 constexpr int kTileM = 128;           // queries per M tile = UMMA M = TMEM lanes
 constexpr int kBlockBytes = 128 * 128;   // one operand K block: 128 rows x 128 bytes (swizzle row) = 16 KB
@@ -188,15 +189,16 @@ struct GemmParams {
 // that operand is 2/3 of what a stage brings in, and the L2 fabric, not the tensor pipe, bounds the pass).  All CTAs of
 // a cluster run the same number of tile iterations (surplus tiles are out-of-range: TMA zero-fills, the epilogue skips).
 template <int KIND, int MT, int EPI, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(threads_of(KIND), 1)
 dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q,
                   const __grid_constant__ CUtensorMap tmap_ql, const GemmParams p) {
     constexpr int NQP = (KIND == kKindTf32x3) ? 2 : 1;            // query operand parts (hi, lo)
     constexpr int kElems = (KIND == kKindTf32x3) ? 32 : 64;       // elements per 128-byte swizzle row
     constexpr int V_BYTES = (KIND == kKindTf32x3) ? 2 * kBlockBytes : kBlockBytes;   // raw corpus block (+ its lo part)
     constexpr int Q_BYTES = MT * NQP * kBlockBytes;               // query blocks of one K block
-    constexpr int kEpiGroups = (KIND == kKindTf32x3) ? 1 : 2;
-    constexpr uint32_t kTmemCols = 2 * MT * kTileN;               // double-buffered accumulators: 256 or 512
+    constexpr int kEpiGroups = (KIND == kKindTf32x3) ? 1 : 4;
+    constexpr int kBufs = (KIND == kKindTf32x3 || MT == 2) ? 2 : 4;                    // accumulator buffers in TMEM
+    constexpr uint32_t kTmemCols = kBufs * MT * kTileN;           // 256 (tf32x3) or 512 columns
 
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte alignment for the 128-byte swizzle atoms
@@ -210,11 +212,11 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
     uint64_t* empty = full + kMaxStages;                          // [stages] MMAs have read the stage
     uint64_t* conv = empty + kMaxStages;                          // [stages] lo part written (tf32x3)
     uint64_t* q_full = conv + kMaxStages;                         // [1]
-    uint64_t* tmem_full = q_full + 1;                             // [2]
-    uint64_t* tmem_empty = tmem_full + 2;                         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* s_inv_vn = reinterpret_cast<float*>(tmem_slot + 2);    // [groups][2][kTileN] 1 / |v_i|
-    float* s_tr = s_inv_vn + 4 * kTileN;                          // STORE: per-warp 32 x 33 transpose tiles
+    uint64_t* tmem_full = q_full + 1;                             // [kBufs <= 4]
+    uint64_t* tmem_empty = tmem_full + 4;                         // [kBufs <= 4]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
+    float* s_inv_vn = reinterpret_cast<float*>(tmem_slot + 2);    // [2][kTileN] 1 / |v_i| (tf32x3)
+    float* s_tr = s_inv_vn + 4 * kTileN;                          // STORE: per-warp 32 x 17-word transpose tiles
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t n_tiles = (p.d1 - p.d0 + kTileN - 1) / kTileN;
@@ -233,9 +235,10 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             mbar_init(&conv[s], 128);          // every converter thread arrives
         }
         mbar_init(q_full, 1);
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < kBufs; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);      // the four epilogue warps that drain the buffer
+            // the epilogue warps that drain the buffer: one group, or two (one per query tile) in bf16 with MT = 2
+            mbar_init(&tmem_empty[a], (KIND == kKindBf16 && MT == 2) ? 8 : 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -297,8 +300,8 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             if (p.q_resident) mbar_wait(q_full, 0);
             int64_t it = 0;
             for (int64_t tile_i = 0; tile_i < n_iter; ++tile_i) {
-                const int buf = (int)(tile_i & 1);
-                mbar_wait(&tmem_empty[buf], (uint32_t)(((tile_i >> 1) & 1) ^ 1));
+                const int buf = (int)(tile_i % kBufs);
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((tile_i / kBufs) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = 0; kb < p.kb; ++kb, ++it) {
                     const int s = (int)(it % p.stages);
@@ -363,37 +366,39 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------ epilogue: thread = query mt * 128 + 32 * (warp % 4) + lane
-        const int grp = (warp - 4) >> 2;                          // bf16: 0 / 1; tf32x3: always 0
+        // ------------------------------------------------ epilogue: a group of four warps drains ONE 128-query accumulator
+        // tile at a time, thread = query 32 * (warp % 4) + lane of that tile.  bf16 runs FOUR groups (the epilogue, not the
+        // tensor pipe or HBM, bounded the pass with two: 2 warps per scheduler cannot hide the TMEM / shared-memory
+        // latencies): with one query tile they take every fourth doc tile (four TMEM buffers), with two query tiles groups
+        // g and g ^ 1 split the two accumulators of the same doc tile (two TMEM buffers).  tf32x3: one group.
+        const int grp = (warp - 4) >> 2;
         const int e = (warp - 4) & 3;                             // TMEM lane quarter = warp id % 4
-        const int etid = e * 32 + lane;                           // 0..127 within the epilogue group
-        float inv_qn[MT], mn[MT], mx[MT], thr[MT];
-        uint32_t n_app[MT];                                       // FILTER: keys appended to this thread's segments
-        uint32_t n_hi[MT], n_lo[MT];                              // STORE + ext: entries of the extreme-candidate lists
-        float g_hi[MT], g_lo[MT], pub_hi[MT], pub_lo[MT];         // ... and the query's max / min over ALL CTAs so far
-        bool active[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int b = mt * kTileM + etid;
-            active[mt] = b < p.nq_valid;
-            inv_qn[mt] = active[mt] ? __ldg(p.inv_qn + b) : 0.f;
-            mn[mt] = __int_as_float(0x7f800000);
-            mx[mt] = __int_as_float(0xff800000);
-            n_app[mt] = 0;
-            n_hi[mt] = n_lo[mt] = 0;
-            g_hi[mt] = pub_hi[mt] = __int_as_float(0xff800000);
-            g_lo[mt] = pub_lo[mt] = __int_as_float(0x7f800000);
-            thr[mt] = (EPI == kEpiFilter && active[mt] && p.thr != nullptr) ? __ldg(p.thr + p.b0 + b)
-                                                                             : __int_as_float(0xff800000);
-        }
-        float* tr = s_tr + (warp - 4) * (32 * 33);                // per-warp 32 x 32 transpose tile (padded)
+        const int etid = e * 32 + lane;                           // 0..127 within the group
+        const int mtg = (MT == 2) ? (grp & 1) : 0;                // query tile of this group
+        const int64_t tile_start = (KIND == kKindTf32x3) ? 0 : (MT == 2 ? (grp >> 1) : grp);
+        constexpr int kTileStep = (KIND == kKindTf32x3) ? 1 : (MT == 2 ? 2 : 4);
+        const int b = mtg * kTileM + etid;                        // query, relative to b0
+        const bool active = b < p.nq_valid;
+        const float inv_qn = active ? __ldg(p.inv_qn + b) : 0.f;
+        float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+        uint32_t n_app = 0;                                       // FILTER: keys appended to this thread's segment
+        uint32_t n_hi = 0, n_lo = 0;                              // STORE + ext: entries of the extreme-candidate lists
+        float g_hi = __int_as_float(0xff800000), pub_hi = g_hi;   // ... and the query's max / min over ALL CTAs so far
+        float g_lo = __int_as_float(0x7f800000), pub_lo = g_lo;
+        const float thr = (EPI == kEpiFilter && active && p.thr != nullptr) ? __ldg(p.thr + p.b0 + b)
+                                                                            : __int_as_float(0xff800000);
+        const int seg = blockIdx.x * kEpiGroups + grp;            // this group's candidate / extreme-list segment
+        const int nrow_raw = p.nq_valid - mtg * kTileM - e * 32;  // live queries of this warp
+        const int nrow = nrow_raw < 0 ? 0 : (nrow_raw > 32 ? 32 : nrow_raw);
+        float* tr = s_tr + (warp - 4) * (32 * 17);                // per-warp 32 x 16-word transpose tile (padded)
+        (void)inv_qn;
         int64_t seq = 0;                                          // tiles this group has drained
-        for (int64_t tile_i = grp; tile_i < n_iter; tile_i += kEpiGroups, ++seq) {
+        for (int64_t tile_i = tile_start; tile_i < n_iter; tile_i += kTileStep, ++seq) {
             const int64_t t = blockIdx.x + tile_i * gridDim.x;
-            const int buf = (int)(tile_i & 1);
+            const int buf = (int)(tile_i % kBufs);
             const int64_t doc0 = p.d0 + t * kTileN;
-            float* inv_vn_tile = s_inv_vn + (grp * 2 + (int)(seq & 1)) * kTileN;   // double-buffered: a warp may
-            if constexpr (KIND != kKindBf16) {                                      // run one tile ahead of its group
+            float* inv_vn_tile = s_inv_vn + (int)(seq & 1) * kTileN;   // double-buffered: a warp may run one tile ahead
+            if constexpr (KIND != kKindBf16) {
                 // 1 / |v_i| of this tile -> smem (zero row -> 0.0, utils.py:49-50).  Not for bf16: its operands are unit
                 // vectors, the accumulator is the cosine.
                 const int64_t d = doc0 + etid;
@@ -403,166 +408,155 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
                     iv = vn != 0.f ? 1.0f / vn : 0.f;
                 }
                 inv_vn_tile[etid] = iv;
-                if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the four warps of this group only
-                else asm volatile("bar.sync 2, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");    // the four warps of the (only) group
             }
-            mbar_wait(&tmem_full[buf], (uint32_t)((tile_i >> 1) & 1));
+            mbar_wait(&tmem_full[buf], (uint32_t)((tile_i / kBufs) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ndoc = (int)((p.d1 - doc0 < kTileN) ? (p.d1 - doc0) : kTileN);
             if constexpr (EPI == kEpiStore) {
                 // extreme-candidate lists: the window hangs off the query's max / min over ALL CTAs so far (published through
                 // the stats slots once per tile), not off this thread's own running extreme -- a per-thread window triggered
                 // in ~4 % of the chunks per thread, i.e. in most chunks per WARP (32 queries), doubling the epilogue
-                if (p.ext != nullptr) {
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
-                        if (active[mt]) {
-                            uint32_t* st = p.stats + (int64_t)(p.b0 + mt * kTileM + etid) * 4;
-                            if (mx[mt] > pub_hi[mt]) {
-                                atomicMax(st + HS_STAT_MAX_A, hs_enc_f32(mx[mt]));
-                                pub_hi[mt] = mx[mt];
-                            }
-                            if (mn[mt] < pub_lo[mt]) {
-                                atomicMin(st + HS_STAT_MIN_A, hs_enc_f32(mn[mt]));
-                                pub_lo[mt] = mn[mt];
-                            }
-                            // fmaxf / fminf drop the NaN an untouched slot decodes to
-                            g_hi[mt] = fmaxf(g_hi[mt], hs_dec_f32(__ldcg(st + HS_STAT_MAX_A)));
-                            g_lo[mt] = fminf(g_lo[mt], hs_dec_f32(__ldcg(st + HS_STAT_MIN_A)));
-                        }
+                if (p.ext != nullptr && active) {
+                    uint32_t* st = p.stats + (int64_t)(p.b0 + b) * 4;
+                    if (mx > pub_hi) {
+                        atomicMax(st + HS_STAT_MAX_A, hs_enc_f32(mx));
+                        pub_hi = mx;
                     }
+                    if (mn < pub_lo) {
+                        atomicMin(st + HS_STAT_MIN_A, hs_enc_f32(mn));
+                        pub_lo = mn;
+                    }
+                    // fmaxf / fminf drop the NaN an untouched slot decodes to
+                    g_hi = fmaxf(g_hi, hs_dec_f32(__ldcg(st + HS_STAT_MAX_A)));
+                    g_lo = fminf(g_lo, hs_dec_f32(__ldcg(st + HS_STAT_MIN_A)));
                 }
             }
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                const int nrow_raw = p.nq_valid - mt * kTileM - e * 32;                  // live queries of this warp
-                const int nrow = nrow_raw < 0 ? 0 : (nrow_raw > 32 ? 32 : nrow_raw);
 #pragma unroll 1
-                for (int c0 = 0; c0 < kTileN; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)((buf * MT + mt) * kTileN + c0), r);
-                    if (c0 >= ndoc || nrow == 0) continue;                  // warp-uniform
-                    // All shared-memory reads of the chunk happen BEFORE any store (the 1 / |v| values as eight 16-byte
-                    // loads into registers), and the scores are computed branch-free: a store inside the per-element loop
-                    // made the compiler keep every later load behind it (possible aliasing through generic pointers), which
-                    // serialised 256 shared-memory round trips per tile and starved the tensor pipe (12 % active).
-                    float v[32];
-                    if constexpr (KIND == kKindBf16) {
+            for (int c0 = 0; c0 < kTileN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(e * 32) << 16) + (uint32_t)((buf * MT + mtg) * kTileN + c0), r);
+                if (c0 >= ndoc || nrow == 0) continue;                  // warp-uniform
+                // All shared-memory reads of the chunk happen BEFORE any store, and the scores are computed branch-free: a
+                // store inside the per-element loop made the compiler keep every later load behind it (possible aliasing
+                // through generic pointers), which serialised 256 shared-memory round trips per tile.
+                float v[32];
+                if constexpr (KIND == kKindBf16) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    } else {
-                        const float4* ivp = reinterpret_cast<const float4*>(inv_vn_tile + c0);
-                        const float qn = inv_qn[mt];
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                } else {
+                    const float4* ivp = reinterpret_cast<const float4*>(inv_vn_tile + c0);
 #pragma unroll
-                        for (int q4 = 0; q4 < 8; ++q4) {
-                            const float4 iv = ivp[q4];
-                            v[4 * q4 + 0] = __uint_as_float(r[4 * q4 + 0]) * iv.x * qn;
-                            v[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) * iv.y * qn;
-                            v[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) * iv.z * qn;
-                            v[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) * iv.w * qn;
-                        }
+                    for (int q4 = 0; q4 < 8; ++q4) {
+                        const float4 iv = ivp[q4];
+                        v[4 * q4 + 0] = __uint_as_float(r[4 * q4 + 0]) * iv.x * inv_qn;
+                        v[4 * q4 + 1] = __uint_as_float(r[4 * q4 + 1]) * iv.y * inv_qn;
+                        v[4 * q4 + 2] = __uint_as_float(r[4 * q4 + 2]) * iv.z * inv_qn;
+                        v[4 * q4 + 3] = __uint_as_float(r[4 * q4 + 3]) * iv.w * inv_qn;
                     }
-                    const int nvalid = ndoc - c0 < 32 ? ndoc - c0 : 32;    // columns of this chunk that are real docs
-                    // chunk extrema first (a tree of 3-input min / max, no per-element predicates on a full chunk): they
-                    // feed the query's running min / max, and the FILTER epilogue tests ONE value against the threshold
-                    float cmn = __int_as_float(0x7f800000), cmx = __int_as_float(0xff800000);
-                    if (nvalid == 32) {
+                }
+                const int nvalid = ndoc - c0 < 32 ? ndoc - c0 : 32;    // columns of this chunk that are real docs
+                // chunk extrema first (a tree of 3-input min / max, no per-element predicates on a full chunk): they
+                // feed the query's running min / max, and the FILTER epilogue tests ONE value against the threshold
+                float cmn = __int_as_float(0x7f800000), cmx = __int_as_float(0xff800000);
+                if (nvalid == 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 32; ++j) {
+                        cmn = fminf(cmn, v[j]);
+                        cmx = fmaxf(cmx, v[j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < nvalid) {
                             cmn = fminf(cmn, v[j]);
                             cmx = fmaxf(cmx, v[j]);
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < nvalid) {
-                                cmn = fminf(cmn, v[j]);
-                                cmx = fmaxf(cmx, v[j]);
-                            }
-                        }
                     }
-                    if (active[mt]) {
-                        mn[mt] = fminf(mn[mt], cmn);
-                        mx[mt] = fmaxf(mx[mt], cmx);
-                    }
-                    if constexpr (EPI == kEpiStore) {
-                        if (p.ext != nullptr && active[mt]) {      // warp-uniform on p.ext; both tests are rare after the first tiles
-                            unsigned long long* lst = p.ext + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
-                                                               (blockIdx.x * kEpiGroups + grp)) * 2 * p.ext_cap;
-                            const float ref_hi = fmaxf(mx[mt], g_hi[mt]) - p.eps2;      // <= (final global max) - eps2
-                            const float ref_lo = fminf(mn[mt], g_lo[mt]) + p.eps2;
-                            if (cmx >= ref_hi) {
+                }
+                if (active) {
+                    mn = fminf(mn, cmn);
+                    mx = fmaxf(mx, cmx);
+                }
+                if constexpr (EPI == kEpiStore) {
+                    if (p.ext != nullptr && active) {      // warp-uniform on p.ext; both tests are rare after the first tiles
+                        unsigned long long* lst = p.ext + ((int64_t)(p.b0 + b) * p.n_seg + seg) * 2 * p.ext_cap;
+                        const float ref_hi = fmaxf(mx, g_hi) - p.eps2;      // <= (final global max) - eps2
+                        const float ref_lo = fminf(mn, g_lo) + p.eps2;
+                        if (cmx >= ref_hi) {
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    if (j < nvalid && v[j] >= ref_hi) {
-                                        if (n_hi[mt] < (uint32_t)p.ext_cap)
-                                            lst[n_hi[mt]] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
-                                        ++n_hi[mt];
-                                    }
-                                }
-                            }
-                            if (cmn <= ref_lo) {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    if (j < nvalid && v[j] <= ref_lo) {
-                                        if (n_lo[mt] < (uint32_t)p.ext_cap)
-                                            lst[p.ext_cap + n_lo[mt]] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
-                                        ++n_lo[mt];
-                                    }
+                            for (int j = 0; j < 32; ++j) {
+                                if (j < nvalid && v[j] >= ref_hi) {
+                                    if (n_hi < (uint32_t)p.ext_cap) lst[n_hi] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
+                                    ++n_hi;
                                 }
                             }
                         }
-                        // transpose through smem so that the global stores run along the docs of ONE query
-                        if (p.cos_h != nullptr) {
-                            // binary16 screen scores, packed BEFORE the transpose: 16 half2 words per query row (row stride 17
-                            // words: conflict-free writes); store instruction i covers rows i and i + 16 (272 words apart =
-                            // the other half of the banks), one half2 = two docs per lane -> 2 x 64 contiguous bytes.
-                            // (Storing straight from the registers -- 16 bytes per ROW and instruction, no transpose -- was
-                            // measured: 3.7x slower, every store instruction touches 32 different lines.)
-                            uint32_t* trh = reinterpret_cast<uint32_t*>(tr);
+                        if (cmn <= ref_lo) {
 #pragma unroll
-                            for (int w = 0; w < 16; ++w) {
-                                const __half2 h = __floats2half2_rn(v[2 * w], v[2 * w + 1]);
-                                trh[lane * 17 + w] = *reinterpret_cast<const uint32_t*>(&h);
-                            }
-                            __syncwarp();
-                            const int sub = lane & 15, rsel = lane >> 4, dcol = c0 + 2 * sub;
-                            __half* dst = p.cos_h + (int64_t)(p.b0 + mt * kTileM + e * 32 + 16 * rsel) * p.cos_ld + (doc0 - p.d0) + dcol;
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) {
-                                if (q + 16 * rsel < nrow) {
-                                    const uint32_t w = trh[(q + 16 * rsel) * 17 + sub];
-                                    if (dcol + 1 < ndoc)
-                                        *reinterpret_cast<uint32_t*>(dst + (int64_t)q * p.cos_ld) = w;
-                                    else if (dcol < ndoc)
-                                        dst[(int64_t)q * p.cos_ld] = __ushort_as_half((unsigned short)(w & 0xFFFFu));
+                            for (int j = 0; j < 32; ++j) {
+                                if (j < nvalid && v[j] <= ref_lo) {
+                                    if (n_lo < (uint32_t)p.ext_cap)
+                                        lst[p.ext_cap + n_lo] = hs_make_key(v[j], (uint32_t)(doc0 + c0 + j));
+                                    ++n_lo;
                                 }
                             }
-                        } else {
+                        }
+                    }
+                    // transpose through smem so that the global stores run along the docs of ONE query.  Store instruction
+                    // i covers rows i and i + 16 of the tile (272 words apart = the other half of the banks; row stride 17
+                    // words: conflict-free writes), 64 contiguous bytes of each.
+                    // (Storing straight from the registers -- 16 bytes per ROW and instruction, no transpose -- was
+                    // measured: 3.7x slower, every store instruction touches 32 different lines.)
+                    const int sub = lane & 15, rsel = lane >> 4;
+                    if (p.cos_h != nullptr) {
+                        // binary16 screen scores, packed BEFORE the transpose: 16 half2 words per query row, one half2 =
+                        // two docs per lane
+                        uint32_t* trh = reinterpret_cast<uint32_t*>(tr);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
-                            __syncwarp();
-                            if (c0 + lane < ndoc) {
-                                float* dst = p.cos + (int64_t)(p.b0 + mt * kTileM + e * 32) * p.cos_ld + (doc0 - p.d0) + c0 + lane;
+                        for (int w = 0; w < 16; ++w) {
+                            const __half2 h = __floats2half2_rn(v[2 * w], v[2 * w + 1]);
+                            trh[lane * 17 + w] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                        __syncwarp();
+                        const int dcol = c0 + 2 * sub;
+                        __half* dst = p.cos_h + (int64_t)(p.b0 + mtg * kTileM + e * 32 + 16 * rsel) * p.cos_ld + (doc0 - p.d0) + dcol;
 #pragma unroll
-                                for (int q = 0; q < 32; ++q)
-                                    if (q < nrow) dst[(int64_t)q * p.cos_ld] = tr[q * 33 + lane];
+                        for (int q = 0; q < 16; ++q) {
+                            if (q + 16 * rsel < nrow) {
+                                const uint32_t w = trh[(q + 16 * rsel) * 17 + sub];
+                                if (dcol + 1 < ndoc)
+                                    *reinterpret_cast<uint32_t*>(dst + (int64_t)q * p.cos_ld) = w;
+                                else if (dcol < ndoc)
+                                    dst[(int64_t)q * p.cos_ld] = __ushort_as_half((unsigned short)(w & 0xFFFFu));
                             }
                         }
                         __syncwarp();
                     } else {
-                        if (active[mt] && cmx >= thr[mt]) {        // rare: some column reaches the query's starting bound
-                            unsigned long long* seg = p.cand + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg +
-                                                                (blockIdx.x * kEpiGroups + grp)) * p.seg_cap;
-                            {
+                        // float32: the 32 columns go through the 16-word tile in two halves
 #pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    if (j < nvalid && v[j] >= thr[mt]) {
-                                        if (n_app[mt] < (uint32_t)p.seg_cap)
-                                            seg[n_app[mt]] = hs_make_key(v[j], p.doc_base + (uint32_t)(doc0 + c0 + j));
-                                        ++n_app[mt];
-                                    }
-                                }
+                        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) tr[lane * 17 + j] = v[16 * h + j];
+                            __syncwarp();
+                            const int dcol = c0 + 16 * h + sub;
+                            if (dcol < ndoc) {
+                                float* dst = p.cos + (int64_t)(p.b0 + mtg * kTileM + e * 32 + 16 * rsel) * p.cos_ld + (doc0 - p.d0) + dcol;
+#pragma unroll
+                                for (int q = 0; q < 16; ++q)
+                                    if (q + 16 * rsel < nrow) dst[(int64_t)q * p.cos_ld] = tr[(q + 16 * rsel) * 17 + sub];
+                            }
+                            __syncwarp();
+                        }
+                    }
+                } else {
+                    if (active && cmx >= thr) {        // rare: some column reaches the query's starting bound
+                        unsigned long long* sg = p.cand + ((int64_t)(p.b0 + b) * p.n_seg + seg) * p.seg_cap;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (j < nvalid && v[j] >= thr) {
+                                if (n_app < (uint32_t)p.seg_cap) sg[n_app] = hs_make_key(v[j], p.doc_base + (uint32_t)(doc0 + c0 + j));
+                                ++n_app;
                             }
                         }
                     }
@@ -572,28 +566,17 @@ dense_gemm_kernel(const __grid_constant__ CUtensorMap tmap_v, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
-        if constexpr (EPI == kEpiFilter) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-                if (active[mt])
-                    p.cand_cnt[(int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg + (blockIdx.x * kEpiGroups + grp)] = n_app[mt];
-        } else if (p.ext != nullptr) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-                if (active[mt]) {
-                    unsigned int* c = p.ext_cnt + ((int64_t)(p.b0 + mt * kTileM + etid) * p.n_seg + (blockIdx.x * kEpiGroups + grp)) * 2;
-                    c[0] = n_hi[mt];
-                    c[1] = n_lo[mt];
-                }
-        }
-        if (p.stats != nullptr) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-                if (active[mt] && mn[mt] <= mx[mt]) {
-                    const int b = p.b0 + mt * kTileM + etid;
-                    atomicMin(&p.stats[b * 4 + HS_STAT_MIN_A], hs_enc_f32(mn[mt]));
-                    atomicMax(&p.stats[b * 4 + HS_STAT_MAX_A], hs_enc_f32(mx[mt]));
-                }
+        if (active) {
+            if constexpr (EPI == kEpiFilter) {
+                p.cand_cnt[(int64_t)(p.b0 + b) * p.n_seg + seg] = n_app;
+            } else if (p.ext != nullptr) {
+                unsigned int* c = p.ext_cnt + ((int64_t)(p.b0 + b) * p.n_seg + seg) * 2;
+                c[0] = n_hi;
+                c[1] = n_lo;
+            }
+            if (p.stats != nullptr && mn <= mx) {
+                atomicMin(&p.stats[(p.b0 + b) * 4 + HS_STAT_MIN_A], hs_enc_f32(mn));
+                atomicMax(&p.stats[(p.b0 + b) * 4 + HS_STAT_MAX_A], hs_enc_f32(mx));
             }
         }
     }
@@ -691,8 +674,8 @@ bool make_plan(int kind, int mt, int epi, int64_t ld_elems, Plan& pl) {
     const int elems = kind == kKindTf32x3 ? 32 : 64;
     const int v_bytes = kind == kKindTf32x3 ? 2 * kBlockBytes : kBlockBytes;
     const int q_blk = mt * nqp * kBlockBytes;
-    const int groups = kind == kKindTf32x3 ? 1 : 2;
-    const int tr = epi == kEpiStore ? groups * 4 * 32 * 33 * 4 : 0;
+    const int groups = kind == kKindTf32x3 ? 1 : 4;
+    const int tr = epi == kEpiStore ? groups * 4 * 32 * 17 * 4 : 0;
     pl.kb = (int)((ld_elems + elems - 1) / elems);
     const int64_t avail = kSmemMax - 1024 - kSmemMisc - tr;
     const int64_t q_all = (int64_t)pl.kb * q_blk;
@@ -716,14 +699,14 @@ int launch_gemm(const CUtensorMap& tv, const CUtensorMap& tq, const CUtensorMap&
     const int64_t n_tiles = (p.d1 - p.d0 + kTileN - 1) / kTileN;
     int grid = (int)(n_tiles < num_sms ? n_tiles : num_sms);
     if (CL == 1) {
-        kern<<<grid, kThreads, smem, st>>>(tv, tq, tql, p);
+        kern<<<grid, threads_of(KIND), smem, st>>>(tv, tq, tql, p);
         HS_LAUNCH_CHECK();
         return HS_OK;
     }
     grid = grid / CL * CL;                      // whole clusters only (callers pick CL > 1 for n_tiles >= num_sms)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.blockDim = dim3(threads_of(KIND), 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -924,7 +907,7 @@ int hs_dense_gemm_ext_f16(const hs_index* idx, const float* queries, int32_t B, 
 
 int32_t hs_dense_gemm_filter_segments(const hs_index* idx, int32_t mode) {
     if (idx == nullptr) return 0;
-    return idx->num_sms * (mode == HS_DENSE_TF32X3 ? 1 : 2);      // one per CTA and epilogue group
+    return idx->num_sms * (mode == HS_DENSE_TF32X3 ? 1 : 4);      // one per CTA and epilogue group
 }
 
 int hs_dense_gemm_filter(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t mode,
