@@ -436,8 +436,7 @@ def run_ours(args):
             if args.dense_mode == "bf16_exact":      # screen (bf16 GEMM) + exact verification: one fused chain
                 qt, qi, qo, n_tok = terms[bi]
                 eng.phase_events = _Marks() if timers is not None else None
-                keys = eng._verified_sub_batch(qd[s:s + nb], nb, stats,
-                                               lambda st_: eng.bm25_score(qt, qi, qo, nb, st_, n_tok), 2, 0.6, 0.4, k,
+                keys = eng._verified_sub_batch(qd[s:s + nb], nb, stats, ("bm25", qt, qi, qo, n_tok), 2, 0.6, 0.4, k,
                                                vflags[s:s + nb], _lib.VERIFY_EPS["bf16_exact"])
                 out = eng.unpack(keys)
                 if timers is not None:               # [start, after GEMM, after BM25, after verify + select + merge]

@@ -63,12 +63,15 @@ SIGNATURES = {
     "hs_cand_select": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _f64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hs_bm25_workspace_bytes": (_sz, [_i64, _i32]),
     "hs_bm25_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "hs_bm25_score_f16": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _vp, _sz, _vp, _i64, _vp, _vp]),
     "hs_bm25plus_score": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _vp, _sz, _vp, _vp, _vp]),
     "hs_bm25_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "hs_bm25plus_score_docs": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _f64, _vp, _vp]),
     "hs_fuse_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "hs_fuse_topk": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _f64, _f64, _i32, _i32, _vp, _vp, _sz, _vp, _vp]),
-    "hs_fuse_topk_f16": (C.c_int, [_vp, _i32, _vp, _vp, _i64, _vp, _f64, _f64, _i32, _i32, _vp, _sz, _vp, _vp]),
+    "hs_fuse_topk_f16": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i64, _vp, _f64, _f64, _i32, _i32, _vp, _sz, _vp, _vp]),
+    "hs_keys_local_docs": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "hs_verify_topk_cand": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _f64, _vp, _f64, _f64, _vp, _i32, _i32, _f64, _vp, _vp, _vp]),
     "hs_topk_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "hs_scatter_keys": (C.c_int, [_vp, _i32, _i32, _i64, _i64, _vp, _vp]),
     "hs_keys_unpack": (C.c_int, [_vp, _i64, _vp, _vp, _vp]),

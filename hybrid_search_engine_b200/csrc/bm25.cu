@@ -24,6 +24,8 @@
 // Algorithmic bytes per query: 8 * P(q) postings + 4 * N doc lengths + 4 * N score store.
 #include "common.cuh"
 
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <cstring>
 
@@ -47,6 +49,8 @@ struct Bm25Params {
     const int32_t* q_off;
     int64_t n_docs, n_terms;
     float* scores;        // [B, n]
+    __half* scores_h;     // batched kernel only: the scores as binary16 [B, ld_h] instead (scores == nullptr) -- the SCREEN
+    int64_t ld_h;         // of the verified mode; the max folded into stats is still that of the float32 values
     uint32_t* stats;      // [B, 4] or null
     int64_t* ranges;      // [n_tokens, n_tiles + 1] posting offsets at every tile boundary (workspace)
     int n_tiles;
@@ -359,6 +363,33 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
         // drains the tile into the score row of query bq: float64 -> float32 once, coalesced store, re-zero, max
         auto epilogue = [&]() {
             float mx = 0.0f;
+            if (p.scores_h != nullptr) {                     // binary16 screen (row stride even, tile start a multiple of 4096)
+                __half* oh = p.scores_h + (int64_t)(b0 + bq) * p.ld_h + d_lo;
+                if (ndoc == kTileDocs) {
+                    double2* a2 = reinterpret_cast<double2*>(sm.acc) + tid;
+                    __half2* o2 = reinterpret_cast<__half2*>(oh) + tid;
+#pragma unroll
+                    for (int r = 0; r < kTileDocs / (2 * kBThreads); ++r) {
+                        const double2 a = a2[r * kBThreads];
+                        a2[r * kBThreads] = make_double2(0.0, 0.0);
+                        const float s0 = __double2float_rn(a.x), s1 = __double2float_rn(a.y);
+                        o2[r * kBThreads] = __floats2half2_rn(s0, s1);
+                        mx = fmaxf(mx, fmaxf(s0, s1));
+                    }
+                } else {
+                    for (int j = tid; j < ndoc; j += kBThreads) {
+                        const float sc = __double2float_rn(sm.acc[j]);
+                        sm.acc[j] = 0.0;
+                        oh[j] = __float2half_rn(sc);
+                        mx = fmaxf(mx, sc);
+                    }
+                }
+#pragma unroll
+                for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, m));
+                if (lane == 0) sm.wmax[warp][bq] = mx;
+                gsync();
+                return;
+            }
             float* o = p.scores + (int64_t)(b0 + bq) * p.n_docs + d_lo;
             if (ndoc == kTileDocs && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {     // group-uniform: full tile
                 double2* a2 = reinterpret_cast<double2*>(sm.acc) + tid;
@@ -719,6 +750,8 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     p.n_docs = idx->n_docs;
     p.n_terms = idx->n_terms;
     p.scores = nullptr;
+    p.scores_h = nullptr;
+    p.ld_h = 0;
     p.stats = nullptr;
     p.ranges = nullptr;
     p.n_tiles = (int)((idx->n_docs + kTileDocs - 1) / kTileDocs);
@@ -794,14 +827,22 @@ size_t hs_bm25_workspace_bytes(int64_t n_docs, int32_t n_tokens) {
 
 static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
                            int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
-                           uint32_t* stats_enc, void* stream, bool plus, double delta) {
+                           uint32_t* stats_enc, void* stream, bool plus, double delta, uint16_t* scores_f16 = nullptr,
+                           int64_t ld_f16 = 0) {
     HS_REQUIRE(idx != nullptr, "hs_bm25_score: idx is null");
     if (idx->n_docs == 0 || B == 0) return HS_OK;
-    HS_REQUIRE(B > 0 && B <= 65535 && scores != nullptr && n_tokens >= 0, "hs_bm25_score: bad arguments (B=%d)", B);
+    HS_REQUIRE(B > 0 && B <= 65535 && (scores != nullptr || scores_f16 != nullptr) && n_tokens >= 0,
+               "hs_bm25_score: bad arguments (B=%d)", B);
+    HS_REQUIRE(scores_f16 == nullptr || (!plus && bm25_use_batch() && ld_f16 >= idx->n_docs && (ld_f16 & 7) == 0 &&
+                                         ((uintptr_t)scores_f16 & 15) == 0),
+               "hs_bm25_score_f16: needs the batched kernel, a 16-byte aligned array and a row stride >= n_docs that is a "
+               "multiple of 8");
     Bm25Params p;
     int rc = fill_params(idx, q_terms, q_idf, q_off, p, "hs_bm25_score");
     if (rc != HS_OK) return rc;
     p.scores = scores;
+    p.scores_h = (__half*)scores_f16;
+    p.ld_h = ld_f16;
     p.stats = stats_enc;
     if (n_tokens > 0) {
         HS_REQUIRE(workspace != nullptr && workspace_bytes >= hs_bm25_workspace_bytes(idx->n_docs, n_tokens),
@@ -857,6 +898,14 @@ int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_i
                   uint32_t* stats_enc, void* stream) {
     return bm25_score_impl(idx, q_terms, q_idf, q_off, B, n_tokens, workspace, workspace_bytes, scores, stats_enc, stream,
                            false, 0.0);
+}
+
+int hs_bm25_score_f16(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                      int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, uint16_t* scores_f16,
+                      int64_t ld, uint32_t* stats_enc, void* stream) {
+    HS_REQUIRE(scores_f16 != nullptr, "hs_bm25_score_f16: scores_f16 is null");
+    return bm25_score_impl(idx, q_terms, q_idf, q_off, B, n_tokens, workspace, workspace_bytes, nullptr, stats_enc, stream,
+                           false, 0.0, scores_f16, ld);
 }
 
 int hs_bm25plus_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,

@@ -167,6 +167,7 @@ struct FuseParams {
     const float* a;
     const __half* a16;    // the a array as IEEE binary16 (the verified mode's SCREEN scores) when a == nullptr
     const float* b;
+    const __half* b16;    // the b array as binary16 [B, ld_a] (hs_bm25_score_f16) when b == nullptr and a16 is set
     const uint32_t* stats;
     const uint64_t* below;
     uint64_t* cand;       // [B, n_chunks, k]
@@ -181,31 +182,69 @@ struct FuseParams {
     double wa64;
 };
 
-// One row of the a array: float32, or binary16 for the screen scores of the verified mode (half the bytes of the
-// GEMM's write and of this pass's read; the rounding is covered by the verification's eps).
-template <bool AH>
-struct ARow;
+// One row of the a / b array: float32, or binary16 for the screen scores of the verified mode (half the bytes of the
+// producer's write and of this pass's read; the rounding is covered by the verification's eps).  load<KD> fetches KD
+// consecutive elements with one 8- or 16-byte instruction.
+__device__ __forceinline__ void hs_unpack_h2(uint32_t w, float& x, float& y) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    x = f.x;
+    y = f.y;
+}
+template <bool H>
+struct FRow;
 template <>
-struct ARow<false> {
+struct FRow<false> {
     const float* p;
-    __device__ __forceinline__ ARow(const FuseParams& fp, int b) : p(fp.a + (int64_t)b * fp.ld_a) {}
+    __device__ __forceinline__ FRow(const float* base, const __half*, int64_t ld, int b)
+        : p(base != nullptr ? base + (int64_t)b * ld : nullptr) {}
+    __device__ __forceinline__ bool present() const { return p != nullptr; }
     __device__ __forceinline__ float at(int64_t i) const { return __ldg(p + i); }
-    __device__ __forceinline__ float4 at4(int64_t i) const { return __ldg(reinterpret_cast<const float4*>(p + i)); }
-    __device__ __forceinline__ bool aligned(int64_t i) const { return (reinterpret_cast<uintptr_t>(p + i) & 15) == 0; }
+    template <int KD>
+    __device__ __forceinline__ void load(int64_t i, float (&o)[KD]) const {
+        static_assert(KD == 4, "float32 rows are read four at a time");
+        if (p == nullptr) {
+            o[0] = o[1] = o[2] = o[3] = 0.f;
+            return;
+        }
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
+        o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+    }
+    template <int KD>
+    __device__ __forceinline__ bool aligned(int64_t i) const {
+        return p == nullptr || (reinterpret_cast<uintptr_t>(p + i) & 15) == 0;
+    }
 };
 template <>
-struct ARow<true> {
+struct FRow<true> {
     const __half* p;
-    __device__ __forceinline__ ARow(const FuseParams& fp, int b) : p(fp.a16 + (int64_t)b * fp.ld_a) {}
+    __device__ __forceinline__ FRow(const float*, const __half* base, int64_t ld, int b) : p(base + (int64_t)b * ld) {}
+    __device__ __forceinline__ bool present() const { return true; }
     __device__ __forceinline__ float at(int64_t i) const { return __half2float(__ldg(p + i)); }
-    __device__ __forceinline__ float4 at4(int64_t i) const {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + i));
-        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    template <int KD>
+    __device__ __forceinline__ void load(int64_t i, float (&o)[KD]) const {
+        static_assert(KD == 4 || KD == 8, "binary16 rows are read four or eight at a time");
+        if constexpr (KD == 4) {
+            const uint2 u = __ldg(reinterpret_cast<const uint2*>(p + i));
+            hs_unpack_h2(u.x, o[0], o[1]);
+            hs_unpack_h2(u.y, o[2], o[3]);
+        } else {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + i));
+            hs_unpack_h2(u.x, o[0], o[1]);
+            hs_unpack_h2(u.y, o[2], o[3]);
+            hs_unpack_h2(u.z, o[4], o[5]);
+            hs_unpack_h2(u.w, o[6], o[7]);
+        }
     }
-    __device__ __forceinline__ bool aligned(int64_t i) const { return (reinterpret_cast<uintptr_t>(p + i) & 7) == 0; }
+    template <int KD>
+    __device__ __forceinline__ bool aligned(int64_t i) const {
+        return (reinterpret_cast<uintptr_t>(p + i) & (KD * 2 - 1)) == 0;
+    }
 };
+// SRC 0: a, b float32; 1: a binary16, b float32 (or absent); 2: a and b binary16
+template <int SRC>
+using ARow = FRow<(SRC >= 1)>;
+template <int SRC>
+using BRow = FRow<(SRC == 2)>;
 
 struct FuseConsts {
     float min_a, range_a, max_b_div, min_b, range_b;
@@ -293,7 +332,7 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
     return v;
 }
 
-template <bool AH>
+template <int SRC>
 __global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParams p) {
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int blk = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -302,14 +341,14 @@ __global__ void __launch_bounds__(kThreads) fuse_blockmax_kernel(const FuseParam
     const int64_t start = (int64_t)blk * stride;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
-    const ARow<AH> pa(p, b);
-    const float* pb = p.b ? p.b + (int64_t)b * p.ld : nullptr;
+    const ARow<SRC> pa(p.a, p.a16, p.ld_a, b);
+    const BRow<SRC> pb(p.b, p.b16, SRC == 2 ? p.ld_a : p.ld, b);
     uint64_t best = 0;
 #pragma unroll
     for (int u = 0; u < kBoundDocs / 32; ++u) {
         const int64_t i = start + u * 32 + lane;
         const float a = pa.at(i);
-        const float bb = pb ? __ldg(pb + i) : 0.f;
+        const float bb = pb.present() ? pb.at(i) : 0.f;
         const uint64_t kk = hs_make_key(fuse_score(p, c, a, bb), (uint32_t)(p.doc_base + i));
         if (kk < below && kk > best) best = kk;
     }
@@ -333,20 +372,22 @@ __global__ void __launch_bounds__(kThreads) fuse_bound_kernel(const FuseParams p
 // any block-wide synchronisation in the loop (loads of consecutive iterations overlap freely); an append
 // that finds the candidate buffer full only raises a flag.  If the flag is up at the end the chunk is
 // redone with the synchronised selector (always correct, used from the start when there is no bound).
-template <int KP, bool AH>
+template <int KP, int SRC>
 __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p) {
     __shared__ Selector<KP> sel;
     __shared__ int overflow;
     constexpr int CAP = Selector<KP>::CAP;
     const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int64_t span = ((p.n + p.n_chunks - 1) / p.n_chunks + kThreads * kItems - 1) / (kThreads * kItems) *
-                         (kThreads * kItems);
+    // docs per CTA: a multiple of the widest vector step (4096 docs: binary16 a and b, 8 per load, 2 loads in flight), so
+    // that only the shard's last chunk has a ragged tail for the element-wise path
+    constexpr int64_t kSpanUnit = kThreads * 16;
+    const int64_t span = ((p.n + p.n_chunks - 1) / p.n_chunks + kSpanUnit - 1) / kSpanUnit * kSpanUnit;
     const int64_t lo = (int64_t)chunk * span;
     const int64_t hi = (lo + span < p.n) ? lo + span : p.n;
     const FuseConsts c = load_consts(p, b);
     const uint64_t below = p.below ? p.below[b] : ~0ull;
-    const ARow<AH> pa(p, b);
-    const float* pb = p.b ? p.b + (int64_t)b * p.ld : nullptr;
+    const ARow<SRC> pa(p.a, p.a16, p.ld_a, b);
+    const BRow<SRC> pb(p.b, p.b16, SRC == 2 ? p.ld_a : p.ld, b);
     unsigned long long* gthr = p.gthr + b;
     if (tid == 0) overflow = 0;
     sel.init();
@@ -364,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
             c0 = c.delta + (c.const_a ? p.wa32 : 0.f);
             if (p.mode == HS_FUSE_HYBRID_BM25) {
                 cb = c.rcp_b * p.wb32;
-            } else if (pb != nullptr) {
+            } else if (pb.present()) {
                 sb = c.const_b ? 0.f : c.min_b;
                 cb = c.const_b ? 0.f : c.rcp_b * p.wb32;
                 c0 += c.const_b ? p.wb32 : 0.f;
@@ -390,36 +431,34 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
                 }
             }
         };
-        constexpr int kV = 2;                                   // 16-byte loads per array, thread and iteration
-        constexpr int kStep = kThreads * 4 * kV;                // 2048 docs per iteration
-        const bool vec_ok = pa.aligned(lo) && (pb == nullptr || (reinterpret_cast<uintptr_t>(pb + lo) & 15) == 0);
+        constexpr int kD = (SRC == 2) ? 8 : 4;                  // docs per vector load
+        constexpr int kV = 2;                                   // vector loads per array, thread and iteration
+        constexpr int kStep = kThreads * kD * kV;               // 2048 / 4096 docs per iteration
+        const bool vec_ok = pa.template aligned<kD>(lo) && pb.template aligned<kD>(lo);
         for (int64_t base = lo; base < hi; base += kStep) {
             if (vec_ok && base + kStep <= hi) {                 // block-uniform
-                float4 a4[kV], b4[kV];
+                float ax[kV][kD], bx[kV][kD];
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
-                    const int64_t i = base + v * (kThreads * 4) + tid * 4;
-                    a4[v] = pa.at4(i);
-                    b4[v] = pb != nullptr ? __ldg(reinterpret_cast<const float4*>(pb + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int64_t i = base + v * (kThreads * kD) + tid * kD;
+                    pa.template load<kD>(i, ax[v]);
+                    pb.template load<kD>(i, bx[v]);
                 }
                 bool cand = false;
 #pragma unroll
-                for (int v = 0; v < kV; ++v) {
-                    const float ax[4] = {a4[v].x, a4[v].y, a4[v].z, a4[v].w}, bx[4] = {b4[v].x, b4[v].y, b4[v].z, b4[v].w};
+                for (int v = 0; v < kV; ++v)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        cand |= !(__fmaf_rn(__fsub_rn(ax[e], sa), ca, __fmaf_rn(__fsub_rn(bx[e], sb), cb, c0)) < thr_f);
-                }
+                    for (int e = 0; e < kD; ++e)
+                        cand |= !(__fmaf_rn(__fsub_rn(ax[v][e], sa), ca, __fmaf_rn(__fsub_rn(bx[v][e], sb), cb, c0)) < thr_f);
                 if (!cand) continue;
                 // rare (about one thread in a thousand): exact keys of this thread's survivors, appended one by one
 #pragma unroll
                 for (int v = 0; v < kV; ++v) {
-                    const float ax[4] = {a4[v].x, a4[v].y, a4[v].z, a4[v].w}, bx[4] = {b4[v].x, b4[v].y, b4[v].z, b4[v].w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (__fmaf_rn(__fsub_rn(ax[e], sa), ca, __fmaf_rn(__fsub_rn(bx[e], sb), cb, c0)) < thr_f) continue;
-                        const int64_t i = base + v * (kThreads * 4) + tid * 4 + e;
-                        const uint64_t kk = hs_make_key(fuse_score(p, c, ax[e], bx[e]), (uint32_t)(p.doc_base + i));
+                    for (int e = 0; e < kD; ++e) {
+                        if (__fmaf_rn(__fsub_rn(ax[v][e], sa), ca, __fmaf_rn(__fsub_rn(bx[v][e], sb), cb, c0)) < thr_f) continue;
+                        const int64_t i = base + v * (kThreads * kD) + tid * kD + e;
+                        const uint64_t kk = hs_make_key(fuse_score(p, c, ax[v][e], bx[v][e]), (uint32_t)(p.doc_base + i));
                         if (kk >= below || kk <= t0) continue;
                         const int pos = atomicAdd(&sel.cnt, 1);
                         if (pos < CAP) sel.buf[pos] = kk;
@@ -429,7 +468,7 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
             } else {                                            // unaligned rows and the ragged tail
                 for (int64_t i0 = base + tid; i0 < base + kStep; i0 += kThreads) {
                     const bool valid = i0 < hi;
-                    consider(valid ? pa.at(i0) : 0.f, (valid && pb != nullptr) ? __ldg(pb + i0) : 0.f, i0, valid);
+                    consider(valid ? pa.at(i0) : 0.f, (valid && pb.present()) ? pb.at(i0) : 0.f, i0, valid);
                 }
             }
         }
@@ -445,7 +484,7 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
             for (int j = 0; j < kItems; ++j) {
                 const int64_t i = base + j * kThreads + tid;
                 av[j] = (i < hi) ? pa.at(i) : 0.f;
-                bv[j] = (pb != nullptr && i < hi) ? __ldg(pb + i) : 0.f;
+                bv[j] = (pb.present() && i < hi) ? pb.at(i) : 0.f;
             }
             // score the current bound stands for (bound 0 = nothing known yet -> -inf)
             const uint64_t t = sel.bound(gthr);
@@ -536,6 +575,17 @@ __global__ void __launch_bounds__(kThreads) topk_merge_walk_kernel(const uint64_
 }
 
 // thr[b] = score of the kth best key of query b (-inf when the list is shorter: no bound)
+// shard-local doc id of every key (-1 for an empty slot or a doc of another shard): the candidate list handed to
+// hs_bm25_score_docs by the verified mode
+__global__ void keys_local_docs_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t doc_base, int64_t n_docs,
+                                       int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = keys[i];
+    const int64_t d = (int64_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFu)) - doc_base;
+    out[i] = (key != 0 && d >= 0 && d < n_docs) ? d : -1;
+}
+
 __global__ void keys_kth_score_kernel(const uint64_t* __restrict__ keys, int B, int k, int kth, float* __restrict__ thr) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -700,8 +750,8 @@ __global__ void __launch_bounds__(kThreads) verify_stats_kernel(const VerifyPara
 template <int KP, int VT>
 __global__ void __launch_bounds__(VT) verify_topk_kernel(const VerifyParams vp, const FuseParams p,
                                                          const uint64_t* __restrict__ approx, int k_sel, int k_out,
-                                                         float eps, uint64_t* __restrict__ out,
-                                                         int32_t* __restrict__ flags) {
+                                                         float eps, const double* __restrict__ b_cand, float eps_b,
+                                                         uint64_t* __restrict__ out, int32_t* __restrict__ flags) {
     static_assert(VT == kThreads || KP / 2 <= kThreads, "bitonic_sort_desc_n strides by kThreads");
     __shared__ uint64_t keys[KP];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -717,7 +767,10 @@ __global__ void __launch_bounds__(VT) verify_topk_kernel(const VerifyParams vp, 
         const uint32_t d = gid - vp.doc_base;
         const float cs = hs_exact_cos_warp(q, qn, vp.v + (int64_t)d * vp.ld, vp.vnorm[d], vp.dim, vp.ld, lane);
         if (lane == 0) {
-            const float bv = p.b != nullptr ? p.b[(int64_t)b * p.ld + d] : 0.f;
+            // the b value: re-computed exactly for the candidate (b_cand, float64 -> the float32 the reference holds), or
+            // read from the exact float32 array
+            const float bv = b_cand != nullptr ? __double2float_rn(b_cand[(int64_t)b * k_sel + i])
+                                               : (p.b != nullptr ? p.b[(int64_t)b * p.ld + d] : 0.f);
             keys[i] = hs_make_key(fuse_score(p, c, cs, bv), gid);
         }
     }
@@ -729,7 +782,8 @@ __global__ void __launch_bounds__(VT) verify_topk_kernel(const VerifyParams vp, 
         const uint64_t last = approx[(int64_t)b * k_sel + k_sel - 1];
         if (last != 0) {                                    // the list is full: there are docs outside it
             const float f_last = hs_dec_f32((uint32_t)(last >> 32));
-            const float delta = c.const_a ? 0.f : fabsf(p.wa32) * eps / c.range_a * 1.001f + 1e-6f;
+            // + the b term's own screen error (binary16 storage of b / max_b: <= eps_b each)
+            const float delta = (c.const_a ? 0.f : fabsf(p.wa32) * eps / c.range_a * 1.001f) + fabsf(p.wb32) * eps_b * 1.001f + 1e-6f;
             const uint64_t kth = keys[k_out - 1];
             const float f_k = kth != 0 ? hs_dec_f32((uint32_t)(kth >> 32)) : -1e30f;
             if (!(f_k > f_last + delta)) atomicOr(flags + b, 2);
@@ -773,21 +827,21 @@ int merge_dispatch(const uint64_t* keys, int n_lists, int B, int k, int64_t list
     return launch_merge<2048>(keys, n_lists, B, k, list_stride, query_stride, out, st);
 }
 
-template <bool AH>
+template <int SRC>
 static void launch_fuse_select(const FuseParams& p, dim3 grid, int B, int k, cudaStream_t st) {
     if (p.n_bound > 0) {
         dim3 bg((unsigned)(p.n_bound / (kThreads / 32)), (unsigned)B);
-        fuse_blockmax_kernel<AH><<<bg, kThreads, 0, st>>>(p);
+        fuse_blockmax_kernel<SRC><<<bg, kThreads, 0, st>>>(p);
         fuse_bound_kernel<<<B, kThreads, 0, st>>>(p);
     }
     if (k <= 128)
-        fuse_topk_kernel<128, AH><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<128, SRC><<<grid, kThreads, 0, st>>>(p);
     else if (k <= 256)
-        fuse_topk_kernel<256, AH><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<256, SRC><<<grid, kThreads, 0, st>>>(p);
     else if (k <= 512)
-        fuse_topk_kernel<512, AH><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<512, SRC><<<grid, kThreads, 0, st>>>(p);
     else
-        fuse_topk_kernel<2048, AH><<<grid, kThreads, 0, st>>>(p);
+        fuse_topk_kernel<2048, SRC><<<grid, kThreads, 0, st>>>(p);
 }
 
 }  // namespace
@@ -799,9 +853,9 @@ size_t hs_fuse_topk_workspace_bytes(int64_t n_docs, int32_t B, int32_t k) {
     return ((size_t)B * n_chunks_for(n_docs, B, k) * (size_t)k + (size_t)B + (size_t)B * kBoundBlocks) * sizeof(uint64_t);
 }
 
-// a: float32 [B, ld], or binary16 [B, ld] when a_half
+// a: float32 [B, ld], or binary16 [B, ld] when a_half; b: float32 [B, n_docs], or binary16 [B, ld] when b_half (a_half too)
 static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t fuse_mode, const void* a, bool a_half,
-                          const float* b, const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
+                          const void* b, bool b_half, const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
                           const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
                           cudaStream_t st) {
     HS_REQUIRE(B > 0 && B <= 65535 && k > 0 && k <= HS_TOPK_MAX, "hs_fuse_topk: B=%d k=%d out of range (k <= %d)", B,
@@ -824,7 +878,8 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
     FuseParams p;
     p.a = a_half ? nullptr : (const float*)a;
     p.a16 = a_half ? (const __half*)a : nullptr;
-    p.b = b;
+    p.b = b_half ? nullptr : (const float*)b;
+    p.b16 = b_half ? (const __half*)b : nullptr;
     p.stats = stats_enc;
     p.below = below_key;
     p.gthr = (unsigned long long*)workspace;
@@ -851,8 +906,9 @@ static int fuse_topk_impl(int64_t n_docs, int64_t doc_base, int64_t ld, int32_t 
             p.n_bound = nb;
             break;
         }
-    if (a_half) launch_fuse_select<true>(p, grid, B, k, st);
-    else launch_fuse_select<false>(p, grid, B, k, st);
+    if (a_half && b_half) launch_fuse_select<2>(p, grid, B, k, st);
+    else if (a_half) launch_fuse_select<1>(p, grid, B, k, st);
+    else launch_fuse_select<0>(p, grid, B, k, st);
     HS_LAUNCH_CHECK();
     // candidate layout [B, n_chunks, k]: list stride k, query stride n_chunks * k
     return merge_dispatch(p.cand, p.n_chunks, B, k, (int64_t)k, (int64_t)p.n_chunks * k, out_keys, st);
@@ -863,23 +919,33 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
                  const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
                  void* stream) {
     HS_REQUIRE(idx != nullptr, "hs_fuse_topk: idx is null");
-    return fuse_topk_impl(idx->n_docs, idx->doc_base, idx->n_docs, fuse_mode, a, false, b, stats_enc, w_a, w_b, B, k,
+    return fuse_topk_impl(idx->n_docs, idx->doc_base, idx->n_docs, fuse_mode, a, false, b, false, stats_enc, w_a, w_b, B, k,
                           below_key, workspace, workspace_bytes, out_keys, (cudaStream_t)stream);
 }
 
-int hs_fuse_topk_f16(const hs_index* idx, int32_t fuse_mode, const uint16_t* a_f16, const float* b, int64_t ld,
-                     const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k, void* workspace,
+int hs_fuse_topk_f16(const hs_index* idx, int32_t fuse_mode, const uint16_t* a_f16, const void* b, int32_t b_is_f16,
+                     int64_t ld, const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k, void* workspace,
                      size_t workspace_bytes, uint64_t* out_keys, void* stream) {
     HS_REQUIRE(idx != nullptr, "hs_fuse_topk_f16: idx is null");
     HS_REQUIRE(fuse_mode != HS_FUSE_RAW, "hs_fuse_topk_f16: screen scores are only fused (SEARCHER / HYBRID_BM25)");
-    return fuse_topk_impl(idx->n_docs, idx->doc_base, ld, fuse_mode, a_f16, true, b, stats_enc, w_a, w_b, B, k, nullptr,
-                          workspace, workspace_bytes, out_keys, (cudaStream_t)stream);
+    HS_REQUIRE(!b_is_f16 || (fuse_mode == HS_FUSE_HYBRID_BM25 && b != nullptr),
+               "hs_fuse_topk_f16: a binary16 b array is the BM25 screen of HS_FUSE_HYBRID_BM25");
+    return fuse_topk_impl(idx->n_docs, idx->doc_base, ld, fuse_mode, a_f16, true, b, b_is_f16 != 0, stats_enc, w_a, w_b, B, k,
+                          nullptr, workspace, workspace_bytes, out_keys, (cudaStream_t)stream);
+}
+
+int hs_keys_local_docs(const uint64_t* keys, int64_t n, int64_t doc_base, int64_t n_docs, int64_t* local_ids, void* stream) {
+    HS_REQUIRE(keys != nullptr && local_ids != nullptr && n >= 0, "hs_keys_local_docs: bad arguments");
+    if (n == 0) return HS_OK;
+    keys_local_docs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keys, n, doc_base, n_docs, local_ids);
+    HS_LAUNCH_CHECK();
+    return HS_OK;
 }
 
 int hs_topk_select(const float* x, int64_t n, int64_t ld, int64_t doc_base, int32_t B, int32_t k, void* workspace,
                    size_t workspace_bytes, uint64_t* out_keys, void* stream) {
     HS_REQUIRE(n >= 0 && doc_base >= 0 && n + doc_base <= 0xFFFFFFFFll, "hs_topk_select: doc ids must fit uint32");
-    return fuse_topk_impl(n, doc_base, ld, HS_FUSE_RAW, x, false, nullptr, nullptr, 1.0, 0.0, B, k, nullptr, workspace,
+    return fuse_topk_impl(n, doc_base, ld, HS_FUSE_RAW, x, false, nullptr, false, nullptr, 1.0, 0.0, B, k, nullptr, workspace,
                           workspace_bytes, out_keys, (cudaStream_t)stream);
 }
 
@@ -950,16 +1016,17 @@ int hs_verify_stats(const hs_index* idx, const float* queries, int32_t B, int64_
     return HS_OK;
 }
 
-int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode, const float* b,
-                   const uint32_t* stats_enc, double w_a, double w_b, const uint64_t* approx_keys, int32_t k_sel,
-                   int32_t k_out, double eps, uint64_t* out_keys, int32_t* flags, void* stream) {
+static int verify_topk_impl(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode,
+                            const float* b, const double* b_cand, double eps_b, const uint32_t* stats_enc, double w_a,
+                            double w_b, const uint64_t* approx_keys, int32_t k_sel, int32_t k_out, double eps,
+                            uint64_t* out_keys, int32_t* flags, void* stream) {
     VerifyParams vp;
     int rc = fill_verify(idx, queries, ld_q, vp, "hs_verify_topk");
     if (rc != HS_OK) return rc;
     if (B == 0) return HS_OK;
     HS_REQUIRE(B > 0 && approx_keys != nullptr && out_keys != nullptr && flags != nullptr && stats_enc != nullptr &&
                    k_out > 0 && k_out <= k_sel && k_sel <= 2048 && eps >= 0.0, "hs_verify_topk: bad arguments");
-    HS_REQUIRE(fuse_mode == HS_FUSE_SEARCHER || (fuse_mode == HS_FUSE_HYBRID_BM25 && b != nullptr),
+    HS_REQUIRE(fuse_mode == HS_FUSE_SEARCHER || (fuse_mode == HS_FUSE_HYBRID_BM25 && (b != nullptr || b_cand != nullptr)),
                "hs_verify_topk: fuse_mode must be SEARCHER or HYBRID_BM25 (with b)");
     FuseParams p;
     memset(&p, 0, sizeof(p));
@@ -974,16 +1041,35 @@ int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t
     p.wa64 = w_a;
     cudaStream_t st = (cudaStream_t)stream;
     if (k_sel <= 128)
-        verify_topk_kernel<128, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+        verify_topk_kernel<128, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, b_cand, (float)eps_b,
+                                                      out_keys, flags);
     else if (k_sel <= 256)
-        verify_topk_kernel<256, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+        verify_topk_kernel<256, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, b_cand, (float)eps_b,
+                                                      out_keys, flags);
     else if (k_sel <= 512)
-        verify_topk_kernel<512, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys, flags);
+        verify_topk_kernel<512, 1024><<<B, 1024, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, b_cand, (float)eps_b,
+                                                      out_keys, flags);
     else
-        verify_topk_kernel<2048, kThreads><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, out_keys,
-                                                                   flags);
+        verify_topk_kernel<2048, kThreads><<<B, kThreads, 0, st>>>(vp, p, approx_keys, k_sel, k_out, (float)eps, b_cand,
+                                                                   (float)eps_b, out_keys, flags);
     HS_LAUNCH_CHECK();
     return HS_OK;
+}
+
+int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode, const float* b,
+                   const uint32_t* stats_enc, double w_a, double w_b, const uint64_t* approx_keys, int32_t k_sel,
+                   int32_t k_out, double eps, uint64_t* out_keys, int32_t* flags, void* stream) {
+    return verify_topk_impl(idx, queries, B, ld_q, fuse_mode, b, nullptr, 0.0, stats_enc, w_a, w_b, approx_keys, k_sel, k_out,
+                            eps, out_keys, flags, stream);
+}
+
+int hs_verify_topk_cand(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode,
+                        const double* b_cand, double eps_b, const uint32_t* stats_enc, double w_a, double w_b,
+                        const uint64_t* approx_keys, int32_t k_sel, int32_t k_out, double eps, uint64_t* out_keys,
+                        int32_t* flags, void* stream) {
+    HS_REQUIRE(b_cand != nullptr && eps_b >= 0.0, "hs_verify_topk_cand: b_cand is null");
+    return verify_topk_impl(idx, queries, B, ld_q, fuse_mode, nullptr, b_cand, eps_b, stats_enc, w_a, w_b, approx_keys, k_sel,
+                            k_out, eps, out_keys, flags, stream);
 }
 
 int hs_topk_merge(const uint64_t* keys, int32_t n_lists, int32_t B, int32_t k, uint64_t* out_keys, void* stream) {

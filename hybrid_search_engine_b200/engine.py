@@ -61,6 +61,12 @@ class SearchEngine:
         self.verify_wide = False   # bf16_exact: re-score 512 instead of 256 candidates per query (set after fallbacks)
         # bf16_exact: keep the screen scores as binary16 (HS_SCREEN_F32=1 restores the float32 screen, an A/B switch)
         self.screen_f16 = os.environ.get("HS_SCREEN_F32", "0") in ("", "0")
+        # bf16_exact: BM25 stored as binary16 too, candidates re-scored exactly (hs_bm25_score_f16 / hs_verify_topk_cand).
+        # OFF by default: measured at 10 M docs x 256 queries it saves 0.33 ms in the BM25 kernel but the binary16 x 2 select
+        # is 0.73 ms slower than the binary16 + float32 one (16.09 vs 15.56 ms per step); HS_SCREEN_BM25_F16=1 turns it on.
+        # Exists in the batched BM25 kernel only (HS_BM25_IMPL=tile selects the A/B kernel).
+        self.screen_bm25_f16 = (os.environ.get("HS_SCREEN_BM25_F16", "0") not in ("", "0")
+                                and os.environ.get("HS_BM25_IMPL", "batch") != "tile")
         self.launches = 0          # kernels launched by this engine (bench.py: gpu_launches)
 
     # ------------------------------------------------------------------ buffers (never on the hot path twice)
@@ -225,11 +231,21 @@ class SearchEngine:
         return n
 
     def bm25_score(self, q_terms, q_idf, q_off, B: int, stats: Optional[torch.Tensor],
-                   n_tokens: Optional[int] = None, plus_delta: Optional[float] = None) -> torch.Tensor:
+                   n_tokens: Optional[int] = None, plus_delta: Optional[float] = None, half: bool = False) -> torch.Tensor:
+        """K1.  ``half``: the scores as binary16 [B, ld] (ld = n_docs rounded up to 8) -- the BM25 screen of the verified
+        mode; the max folded into ``stats`` is the float32 one either way."""
         n_tokens = self._n_tokens if n_tokens is None else int(n_tokens)
-        sc = self._buf("bm25", (B, self.shard.n_docs), torch.float32)
         nbytes = self.lib.hs_bm25_workspace_bytes(self.shard.n_docs, n_tokens)
         ws = self._buf("bm25_ws", (max(nbytes // 8, 1),), torch.int64)
+        if half:
+            ld_h = (self.shard.n_docs + 7) // 8 * 8
+            sc = self._buf("bm25_h", (B, ld_h), torch.float16)
+            check(self.lib.hs_bm25_score_f16(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, n_tokens,
+                                             ptr(ws), nbytes, ptr(sc), ld_h, ptr(stats), stream_ptr(self.device)),
+                  "hs_bm25_score_f16")
+            self.launches += 2 if n_tokens > 0 else 1
+            return sc
+        sc = self._buf("bm25", (B, self.shard.n_docs), torch.float32)
         if plus_delta is not None:
             check(self.lib.hs_bm25plus_score(self.shard.handle, ptr(q_terms), ptr(q_idf), ptr(q_off), B, n_tokens,
                                              float(plus_delta), ptr(ws), nbytes, ptr(sc), ptr(stats),
@@ -528,7 +544,14 @@ class SearchEngine:
             check(self.lib.hs_dense_gemm_ext(self.shard.handle, ptr(qd), nb, qd.stride(0), m, 0, n, wsp, nbytes, ptr(cos), n,
                                              ptr(stats), ptr(ext), ptr(ext_cnt), cap, float(eps), st), "hs_dense_gemm_ext")
         mark()
-        b = bm(stats) if callable(bm) else bm
+        # b array: a float32 lexical vector given by the caller, or ("bm25", q_terms, q_idf, q_off, n_tokens) -> BM25 scored
+        # here; with the binary16 screen BM25 is stored as binary16 too and re-scored exactly for the candidates below
+        terms = bm[1:] if isinstance(bm, tuple) else None
+        b_half = terms is not None and f16 and self.screen_bm25_f16
+        if terms is not None:
+            b = self.bm25_score(terms[0], terms[1], terms[2], nb, stats, terms[3], half=b_half)
+        else:
+            b = bm
         mark()
         check(self.lib.hs_verify_stats(self.shard.handle, ptr(qd), nb, qd.stride(0), ptr(ext), ptr(ext_cnt), n_seg, cap,
                                        float(eps), ptr(stats), ptr(flags), st), "hs_verify_stats")
@@ -543,16 +566,31 @@ class SearchEngine:
             ws_bytes = self.lib.hs_fuse_topk_workspace_bytes(n, nb, k_sel)
             ws = self._buf("topk_ws", (max(ws_bytes // 8, 1),), torch.int64)
             approx = self._buf("vkeys", (nb, k_sel), torch.int64)
-            check(self.lib.hs_fuse_topk_f16(self.shard.handle, mode, ptr(cos), ptr(b), cos.stride(0), ptr(stats), float(wa),
-                                            float(wb), nb, k_sel, ptr(ws), ws_bytes, ptr(approx), st), "hs_fuse_topk_f16")
+            check(self.lib.hs_fuse_topk_f16(self.shard.handle, mode, ptr(cos), ptr(b), 1 if b_half else 0, cos.stride(0),
+                                            ptr(stats), float(wa), float(wb), nb, k_sel, ptr(ws), ws_bytes, ptr(approx), st),
+                  "hs_fuse_topk_f16")
             self.launches += 2
         else:
             approx = self.fuse_topk(mode, cos, b, stats, wa, wb, k_sel, merge=False, out="vkeys")
         mark("select")
         keys = self._buf("keys", (nb, k), torch.int64)
-        check(self.lib.hs_verify_topk(self.shard.handle, ptr(qd), nb, qd.stride(0), mode, ptr(b), ptr(stats), float(wa),
-                                      float(wb), ptr(approx), k_sel, k, float(eps), ptr(keys), ptr(flags), st),
-              "hs_verify_topk")
+        if b_half:
+            # exact BM25 of the candidates only: key list -> shard-local doc ids -> BM25.score (float64, token order)
+            cand = self._buf("vcand", (nb, k_sel), torch.int64)
+            check(self.lib.hs_keys_local_docs(ptr(approx), nb * k_sel, self.shard.doc_base, n, ptr(cand), st),
+                  "hs_keys_local_docs")
+            b_cand = self._buf("vcand_bm", (nb, k_sel), torch.float64)
+            check(self.lib.hs_bm25_score_docs(self.shard.handle, ptr(terms[0]), ptr(terms[1]), ptr(terms[2]), nb, ptr(cand),
+                                              k_sel, ptr(b_cand), st), "hs_bm25_score_docs")
+            mark("rescore_bm25")
+            check(self.lib.hs_verify_topk_cand(self.shard.handle, ptr(qd), nb, qd.stride(0), mode, ptr(b_cand),
+                                               float(_lib.SCREEN_F16_EPS), ptr(stats), float(wa), float(wb), ptr(approx),
+                                               k_sel, k, float(eps), ptr(keys), ptr(flags), st), "hs_verify_topk_cand")
+            self.launches += 2
+        else:
+            check(self.lib.hs_verify_topk(self.shard.handle, ptr(qd), nb, qd.stride(0), mode, ptr(b), ptr(stats), float(wa),
+                                          float(wb), ptr(approx), k_sel, k, float(eps), ptr(keys), ptr(flags), st),
+                  "hs_verify_topk")
         self.launches += 2 * self._gemm_passes(nb, m) + 3
         mark("verify_topk")
         keys = self._merge_across(keys)
@@ -607,7 +645,7 @@ class SearchEngine:
                 if verify:
                     if use_bm25:
                         qt, qi, qo, n_tok = terms_all[bi]
-                        bm = (lambda st_, a=(qt, qi, qo, nb, n_tok): self.bm25_score(a[0], a[1], a[2], a[3], st_, a[4]))
+                        bm = ("bm25", qt, qi, qo, n_tok)
                     keys = self._verified_sub_batch(qd_all[s:e], nb, stats, bm, mode, wa, wb, k, flags[s:e], eps)
                 else:
                     if mode != HS_FUSE_RAW:

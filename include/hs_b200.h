@@ -156,6 +156,14 @@ int hs_verify_stats(const hs_index* idx, const float* queries, int32_t B, int64_
 int hs_verify_topk(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode, const float* b,
                    const uint32_t* stats_enc, double w_a, double w_b, const uint64_t* approx_keys, int32_t k_sel,
                    int32_t k_out, double eps, uint64_t* out_keys, int32_t* flags, void* stream);
+/* hs_verify_topk for a select that screened BOTH arrays in binary16 (HS_FUSE_HYBRID_BM25): the b value of candidate i
+ * of query q is b_cand[q * k_sel + i], recomputed exactly for the listed docs (hs_keys_local_docs + hs_bm25_score_docs:
+ * the float64 BM25 sum, rounded here to the float32 the reference holds, bm25.py:124-126); eps_b bounds the screen's
+ * error on b / max_b (2^-11 for binary16) and widens the soundness margin by |w_b| eps_b. */
+int hs_verify_topk_cand(const hs_index* idx, const float* queries, int32_t B, int64_t ld_q, int32_t fuse_mode,
+                        const double* b_cand, double eps_b, const uint32_t* stats_enc, double w_a, double w_b,
+                        const uint64_t* approx_keys, int32_t k_sel, int32_t k_out, double eps, uint64_t* out_keys,
+                        int32_t* flags, void* stream);
 /* the same GEMM with the select's pre-filter fused into its epilogue (pure-semantic retrieval: Searcher.search with
  * lexical weight 0, multi_stage stage 1, pipelines.py:474-481): nothing is stored; every (query, doc) cosine >=
  * thr[b] (NULL: all) is appended as a ranking key to the query's candidate lists.  No atomics: each (CTA, epilogue
@@ -176,6 +184,12 @@ size_t hs_bm25_workspace_bytes(int64_t n_docs, int32_t n_tokens);
 int hs_bm25_score(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
                   int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, float* scores,
                   uint32_t* stats_enc, void* stream);
+/* the same scores stored as IEEE binary16 [B, ld] (ld >= n_docs, a multiple of 8; 16-byte aligned): the BM25 SCREEN of the
+ * verified mode -- half the bytes written here and re-read by hs_fuse_topk_f16.  The max folded into stats is that of
+ * the float32 scores (exact, pipelines.py:332); exact values of the candidates come from hs_bm25_score_docs. */
+int hs_bm25_score_f16(const hs_index* idx, const int32_t* q_terms, const double* q_idf, const int32_t* q_off,
+                      int32_t B, int32_t n_tokens, void* workspace, size_t workspace_bytes, uint16_t* scores_f16,
+                      int64_t ld, uint32_t* stats_enc, void* stream);
 
 /* BM25Plus.score over all docs (bm25.py:150-179): idf * (num / den + delta) for EVERY doc and known query
  * token (dense variant, used by no pipeline); same arguments as hs_bm25_score plus delta */
@@ -206,11 +220,16 @@ int hs_fuse_topk(const hs_index* idx, int32_t fuse_mode, const float* a, const f
                  const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k,
                  const uint64_t* below_key, void* workspace, size_t workspace_bytes, uint64_t* out_keys,
                  void* stream);
-/* hs_fuse_topk whose a array is the binary16 screen of hs_dense_gemm_ext_f16 (row stride ld elements; b float32 [B, n_docs]):
- * the approximate select of the verified mode (fuse_mode SEARCHER or HYBRID_BM25; results go to hs_verify_topk). */
-int hs_fuse_topk_f16(const hs_index* idx, int32_t fuse_mode, const uint16_t* a_f16, const float* b, int64_t ld,
-                     const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k, void* workspace,
+/* hs_fuse_topk whose a array is the binary16 screen of hs_dense_gemm_ext_f16 (row stride ld elements): the approximate
+ * select of the verified mode (fuse_mode SEARCHER or HYBRID_BM25; results go to hs_verify_topk / hs_verify_topk_cand).
+ * b: float32 [B, n_docs] (b_is_f16 = 0), or the binary16 BM25 screen of hs_bm25_score_f16, [B, ld] (b_is_f16 = 1,
+ * HS_FUSE_HYBRID_BM25 only). */
+int hs_fuse_topk_f16(const hs_index* idx, int32_t fuse_mode, const uint16_t* a_f16, const void* b, int32_t b_is_f16,
+                     int64_t ld, const uint32_t* stats_enc, double w_a, double w_b, int32_t B, int32_t k, void* workspace,
                      size_t workspace_bytes, uint64_t* out_keys, void* stream);
+/* local_ids[i] = shard-local doc id of keys[i], -1 for an empty slot (key 0) or a doc outside [doc_base, doc_base + n_docs):
+ * turns a key list into the candidate list of hs_bm25_score_docs */
+int hs_keys_local_docs(const uint64_t* keys, int64_t n, int64_t doc_base, int64_t n_docs, int64_t* local_ids, void* stream);
 /* top_k_indices (utils.py:74-87) of a float32 [B, n] array with row stride ld that is not a whole shard (e.g. the
  * sample block of the filtered tensor-core scan): keys carry doc_base + position */
 int hs_topk_select(const float* x, int64_t n, int64_t ld, int64_t doc_base, int32_t B, int32_t k, void* workspace,

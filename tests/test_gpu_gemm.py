@@ -207,6 +207,12 @@ def test_bf16_exact_mode_is_bit_identical_to_exact(hs, B, k):
     want = [t.cpu().numpy().copy() for t in eng.search_searcher(qs, lex, k, 0.7, 0.3, dense_mode="exact")]
     assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
     print(f"bf16_exact: {getattr(eng, 'verify_fallbacks', 0)} of {2 * B + lex.shape[0]} queries fell back to the exact mode")
+    # BM25 screened in binary16 as well, candidates re-scored exactly (HS_SCREEN_BM25_F16=1; off by default)
+    eng.max_batch, eng.screen_bm25_f16 = 256, True
+    got = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="bf16_exact")]
+    eng.max_batch, eng.screen_bm25_f16 = 8, False
+    want = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="exact")]
+    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
     # the float32 screen (HS_SCREEN_F32=1; the default keeps the screen scores as binary16) proves the same result
     eng.max_batch, eng.screen_f16 = 256, False
     got = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="bf16_exact")]
@@ -227,9 +233,11 @@ def test_bf16_exact_ragged_shard_sizes(hs, n_docs):
     B, k = 37, 20
     qb = QueryBatch(vectors=synth.query_embeddings(spec, 0, B), term_ids=synth.query_terms(spec, 0, B, th).tolist())
     eng = SearchEngine(shard, max_batch=64)
-    got = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="bf16_exact")]
     want = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="exact")]
-    assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0])
+    for bm25_f16 in (False, True):
+        eng.screen_bm25_f16 = bm25_f16
+        got = [t.cpu().numpy().copy() for t in eng.search_hybrid_bm25(qb, k, 0.6, 0.4, dense_mode="bf16_exact")]
+        assert np.array_equal(got[1], want[1]) and np.array_equal(got[0], want[0]), bm25_f16
 
 
 def test_bf16_exact_pipeline_matches_oracle_on_real_text(hs):
