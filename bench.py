@@ -657,7 +657,9 @@ def run_ours(args):
         elem = 4
         if args.dense_mode in ("bf16", "bf16_exact"):
             elem = 2
-        dense_bytes = n_shard * shard.ld * elem * passes + (B * n_shard * 4 if tensor_mode else 0)
+        # + the score matrix the tensor-core modes write: float32, or binary16 for the screen of bf16_exact
+        f16_screen = args.dense_mode == "bf16_exact" and eng.screen_f16
+        dense_bytes = n_shard * shard.ld * elem * passes + (B * n_shard * (2 if f16_screen else 4) if tensor_mode else 0)
         gname = {"bf16_exact": "bf16 STORE + extreme lists"}.get(args.dense_mode, args.dense_mode)
         ent = {"name": "dense_gemm_kernel (tcgen05 %s)" % gname if tensor_mode else "dense_scan_kernel",
                "ms_per_step": dense_ms, "launches_per_step": passes, "alg_bytes_per_step": dense_bytes,
@@ -683,6 +685,8 @@ def run_ours(args):
         kernels.append({"name": "bm25_ranges_kernel + bm25_batch_kernel", "ms_per_step": bm25_ms, "alg_bytes_per_step": bm_bytes,
                         "postings_per_step": P, "hbm_GBps": bm_bytes / bm25_ms / 1e6, "frac_hbm": bm_bytes / bm25_ms / 1e6 / hbm_peak})
         sel_bytes = (8 if wl == "hybrid" else 4) * n_shard * B
+        if wl == "hybrid" and args.dense_mode == "bf16_exact" and eng.screen_f16:
+            sel_bytes = ((4 if eng.screen_bm25_f16 else 6)) * n_shard * B      # binary16 screen + float32 (or binary16) BM25
         sname = "fuse_blockmax + fuse_bound + fuse_topk + topk_merge + keys_unpack"
         if args.dense_mode == "bf16_exact" and wl == "hybrid":
             sname = "verify_stats + fuse_blockmax + fuse_bound + fuse_topk (k' = 256) + topk_merge + verify_topk + keys_unpack"
@@ -724,8 +728,11 @@ def run_ours(args):
     roof.update({"peak_source": peak_src, "traffic": None, "kernels": kernels})
     try:    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture, when one matches
         ent = json.load(open(os.path.join(ROOT, "profiles", "dense_traffic.json")))["entries"]
-        roof["traffic"] = ent.get(f"{args.dense_mode}_n{n_shard}_ld{shard.ld}_q{sub}") if tensor_mode else \
-            ent.get(f"n{n_shard}_ld{shard.ld}_q{min(sub, 8)}")
+        if "bm25_batch" in str(roof.get("kernel", "")):      # the dominant kernel is BM25: its own capture
+            roof["traffic"] = ent.get(f"bm25_batch_n{n_shard}_q{B}")
+        else:
+            roof["traffic"] = ent.get(f"{args.dense_mode}_n{n_shard}_ld{shard.ld}_q{sub}") if tensor_mode else \
+                ent.get(f"n{n_shard}_ld{shard.ld}_q{min(sub, 8)}")
     except Exception:
         pass
 

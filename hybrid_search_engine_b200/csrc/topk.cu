@@ -95,6 +95,12 @@ struct Selector {
         }
         __syncthreads();
     }
+    // after init(), for a pass that only appends (no prune): no slots reserved for a "current best", every slot beyond
+    // cnt stays zero.  Collective.
+    __device__ void start_empty() {
+        if (threadIdx.x == 0) cnt = 0;
+        __syncthreads();
+    }
     __device__ __forceinline__ uint64_t bound(const unsigned long long* shared_thr) const {
         uint64_t t = thr;
         if (shared_thr != nullptr) {
@@ -153,9 +159,11 @@ struct Selector {
     }
     // final ordering: only slots [0, cnt) can hold keys that matter (slots beyond were discarded by an
     // earlier prune), so sort the smallest power of two covering them
+    // (A CTA that never pruned may hold just a handful of keys -- start_empty() -- and sorts 32 slots instead of 2 KP:
+    // with a starting bound the final sort, not the scan, was most of what the select kernel executed.)
     __device__ void finish(int k) {
         int used = cnt < CAP ? cnt : CAP;
-        int n = KP;
+        int n = 32;
         while (n < used) n <<= 1;
         for (int i = used + threadIdx.x; i < n; i += kThreads) buf[i] = 0;   // stale keys below the cut
         __syncthreads();
@@ -394,6 +402,7 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
     const uint64_t t0 = sel.bound(gthr);
     bool redo = (t0 == 0);                                   // no bound: go straight to the safe path
     if (!redo) {
+        sel.start_empty();
         const float thr_f = hs_dec_f32((uint32_t)(t0 >> 32));
         // per-thread pre-filter: the estimate of fuse_score_estimate as one subtract and two FMAs per element,
         // (a - sa) * ca + ((b - sb) * cb + c0) with the margin folded into c0.  A thread whose 8 elements all
