@@ -59,6 +59,7 @@ struct Bm25Params {
     // once per index (hs_bm25_build_hot).  The batched kernel streams it like a posting chunk and adds it slot by slot
     const double* hot_c;         // [n_hot, n_docs]; 0.0 where the doc does not hold the term
     const int32_t* hot_of_term;  // [n_terms] -> row of hot_c, or -1
+    int pf;                      // batched kernel: L2 prefetch distance in chunks
 };
 
 // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (dl / avgdl))), or 0 where the reference adds 0 (den <= 0):
@@ -560,13 +561,15 @@ __global__ void __launch_bounds__(kBThreads* kGroups, 1)
             const int nC = sm.n_chunks;
             uint2 A[kDepth], Bf[kDepth];
             if (nC > 0) load_chunk(sm.chunk[0], A);
-            if (nC > 1) prefetch_chunk(1);
+            // L2 prefetch distance p.pf (chunks ahead of the one being consumed; HS_BM25_PF, default 2)
+            const int kPf = p.pf;
+            for (int c = 1; c < kPf + 1 && c < nC; ++c) prefetch_chunk(c);
             for (int i = 0; i < nC; i += 2) {
-                if (i + 2 < nC) prefetch_chunk(i + 2);
+                if (i + kPf < nC) prefetch_chunk(i + kPf);
                 if (i + 1 < nC) load_chunk(sm.chunk[i + 1], Bf);
                 consume(i, A);
                 if (i + 1 >= nC) break;
-                if (i + 3 < nC) prefetch_chunk(i + 3);
+                if (i + kPf + 1 < nC) prefetch_chunk(i + kPf + 1);
                 if (i + 2 < nC) load_chunk(sm.chunk[i + 2], A);
                 consume(i + 1, Bf);
             }
@@ -752,6 +755,8 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     p.scores = nullptr;
     p.scores_h = nullptr;
     p.ld_h = 0;
+    static const int pf_env = getenv("HS_BM25_PF") != nullptr ? atoi(getenv("HS_BM25_PF")) : 2;
+    p.pf = pf_env < 1 ? 1 : (pf_env > 16 ? 16 : pf_env);
     p.stats = nullptr;
     p.ranges = nullptr;
     p.n_tiles = (int)((idx->n_docs + kTileDocs - 1) / kTileDocs);
