@@ -60,6 +60,7 @@ struct Bm25Params {
     const double* hot_c;         // [n_hot, n_docs]; 0.0 where the doc does not hold the term
     const int32_t* hot_of_term;  // [n_terms] -> row of hot_c, or -1
     int pf;                      // batched kernel: L2 prefetch distance in chunks
+    int skip_hot;                // ranges kernel: hot terms need no posting offsets (the batched kernel streams hot_c)
 };
 
 // (tf * (k1 + 1)) / (tf + k1 * (1 - b + b * (dl / avgdl))), or 0 where the reference adds 0 (den <= 0):
@@ -661,6 +662,12 @@ __global__ void bm25_ranges_kernel(const Bm25Params p, int n_tokens) {
     const int term = p.q_terms[tok];
     int64_t r = 0;
     if (term >= 0 && term < p.n_terms) {
+        if (p.skip_hot && __ldg(p.hot_of_term + term) >= 0) {
+            // a hot term: the batched kernel only tests "slice not empty" before it takes the dense vector's slice (a
+            // tile without a posting of the term adds zeros: same bits) -- no search, offsets j, j + 1, ...
+            if (lane == 0) p.ranges[w] = j;
+            return;
+        }
         const int64_t pl = p.indptr[term], ph = p.indptr[term + 1];
         if (j == 0) r = pl;
         else if (j == p.n_tiles) r = ph;
@@ -757,6 +764,7 @@ int fill_params(const hs_index* idx, const int32_t* q_terms, const double* q_idf
     p.ld_h = 0;
     static const int pf_env = getenv("HS_BM25_PF") != nullptr ? atoi(getenv("HS_BM25_PF")) : 2;
     p.pf = pf_env < 1 ? 1 : (pf_env > 16 ? 16 : pf_env);
+    p.skip_hot = 0;
     p.stats = nullptr;
     p.ranges = nullptr;
     p.n_tiles = (int)((idx->n_docs + kTileDocs - 1) / kTileDocs);
@@ -853,6 +861,7 @@ static int bm25_score_impl(const hs_index* idx, const int32_t* q_terms, const do
         HS_REQUIRE(workspace != nullptr && workspace_bytes >= hs_bm25_workspace_bytes(idx->n_docs, n_tokens),
                    "hs_bm25_score: workspace too small");
         p.ranges = (int64_t*)workspace;
+        p.skip_hot = (!plus && bm25_use_batch() && p.hot_of_term != nullptr) ? 1 : 0;
         const int64_t warps = (int64_t)n_tokens * (p.n_tiles + 1);
         bm25_ranges_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n_tokens);
         HS_LAUNCH_CHECK();
