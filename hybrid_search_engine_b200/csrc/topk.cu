@@ -802,15 +802,18 @@ __global__ void __launch_bounds__(VT) verify_topk_kernel(const VerifyParams vp, 
 
 // CTAs (= candidate lists of k keys) per query.  Every list costs k keys of output, a sort and a slot in the merge,
 // whatever its doc range: on a small shard with a large k (doc-sharded runs, the 256 / 512-key lists of the verified
-// mode) 296 lists of a few thousand docs made the select chain a FIXED cost.  So: at least 128 k docs per list (at 64 k
-// a 5 M-doc shard ran the 256-key select at 0.62 of HBM against 0.80 for the 10 M one), but enough CTAs over the batch
-// to fill the GPU twice, at most 296, at least 4096 docs each.
+// mode) 296 lists of a few thousand docs made the select chain a FIXED cost.  So: at least 512 k docs per list (measured
+// at 10 M docs x 256 queries, k = 256: 64 k -> 128 k -> 512 k docs per list = 0.62 -> 0.80 -> 0.88 of HBM for the main
+// pass), but at least 8 x 296 CTAs over the batch, at most 296 lists, at least 4096 docs each.
+// HS_TOPK_LIST_MULT / HS_TOPK_FILL override the two factors (A/B runs).
 int n_chunks_for(int64_t n, int B, int k) {
     int64_t cap = (n + kChunkDocs - 1) / kChunkDocs;
     if (cap > kMaxChunks) cap = kMaxChunks;
     if (cap < 1) cap = 1;
-    int64_t c = n / ((int64_t)128 * (k > 0 ? k : 1));
-    const int64_t fill = (2 * kMaxChunks + (B > 0 ? B : 1) - 1) / (B > 0 ? B : 1);
+    static const int64_t mult = getenv("HS_TOPK_LIST_MULT") != nullptr ? atoll(getenv("HS_TOPK_LIST_MULT")) : 512;
+    int64_t c = n / ((mult > 0 ? mult : 512) * (k > 0 ? k : 1));
+    static const int64_t fillx = getenv("HS_TOPK_FILL") != nullptr ? atoll(getenv("HS_TOPK_FILL")) : 8;
+    const int64_t fill = ((fillx > 0 ? fillx : 8) * kMaxChunks + (B > 0 ? B : 1) - 1) / (B > 0 ? B : 1);
     if (c < fill) c = fill;
     if (c > cap) c = cap;
     if (c < 1) c = 1;
