@@ -397,9 +397,15 @@ __global__ void __launch_bounds__(kThreads) fuse_topk_kernel(const FuseParams p)
     const ARow<SRC> pa(p.a, p.a16, p.ld_a, b);
     const BRow<SRC> pb(p.b, p.b16, SRC == 2 ? p.ld_a : p.ld, b);
     unsigned long long* gthr = p.gthr + b;
+    __shared__ uint64_t t0_shared;
     if (tid == 0) overflow = 0;
     sel.init();
-    const uint64_t t0 = sel.bound(gthr);
+    // ONE read of the published bound per CTA: other CTAs of the query publish concurrently (atomicMax in prune), and threads
+    // that read different values would split between the two paths below, whose barriers differ (an intermittent
+    // cudaErrorIllegalInstruction for k > 512, where no bound kernel publishes before this kernel starts)
+    if (tid == 0) t0_shared = sel.bound(gthr);
+    __syncthreads();
+    const uint64_t t0 = t0_shared;
     bool redo = (t0 == 0);                                   // no bound: go straight to the safe path
     if (!redo) {
         sel.start_empty();

@@ -288,3 +288,28 @@ def test_bf16_exact_falls_back_when_the_bound_cannot_be_proven(hs):
     assert eng.verify_fallbacks >= sum(sizes) // 2, eng.verify_fallbacks
     for (gs, gi), (ws_, wi) in zip(got, want):
         assert np.array_equal(gi, wi) and np.array_equal(gs, ws_)
+
+
+def test_large_k_select_with_many_lists_is_stable(hs):
+    """k > 512 runs the select without a pre-computed bound: the first bound is published by the query's own CTAs while later
+    CTAs start.  Every CTA must read it ONCE (a per-thread read split a CTA between two code paths with different barriers:
+    an intermittent cudaErrorIllegalInstruction once a query had more CTAs than fit on the GPU at a time).  40 repetitions of
+    the call that used to fail 1 time in ~15, each equal to the first."""
+    from hybrid_search_engine_b200 import synth, synth_device
+    from hybrid_search_engine_b200.engine import QueryBatch, SearchEngine
+    spec = synth.SynthSpec(n_docs=300_000, vocab=50_000, dim=96)
+    shard = synth_device.build_synthetic_shard(spec, 0, spec.n_docs, torch.device("cuda:0"), lexical=False)
+    B, k = 130, 400
+    qv = synth.query_embeddings(spec, 0, B)
+    qv[5] = 0.0
+    eng = SearchEngine(shard, max_batch=256)
+    first = None
+    for _ in range(40):
+        s, i = eng.search_semantic(QueryBatch(vectors=qv), k, 0.7, dense_mode="bf16_exact")
+        got = (s.cpu().numpy().copy(), i.cpu().numpy().copy())
+        if first is None:
+            first = got
+        assert np.array_equal(got[1], first[1]) and np.array_equal(got[0], first[0])
+    eng.max_batch = 8
+    s, i = eng.search_semantic(QueryBatch(vectors=qv), k, 0.7, dense_mode="exact")
+    assert np.array_equal(i.cpu().numpy(), first[1]) and np.array_equal(s.cpu().numpy(), first[0])
