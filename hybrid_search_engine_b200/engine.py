@@ -283,8 +283,17 @@ class SearchEngine:
         check(self.lib.hs_fuse_topk(self.shard.handle, mode, ptr(a), ptr(b), ptr(stats), float(wa), float(wb),
                                     B, k, ptr(below), ptr(ws), ws_bytes, ptr(keys), stream_ptr(self.device)),
               "hs_fuse_topk")
-        self.launches += 2 if n > 0 else 0
+        self.launches += self._select_launches(n, k)
         return self._merge_across(keys) if merge else keys
+
+    @staticmethod
+    def _select_launches(n: int, k: int) -> int:
+        """Kernels one hs_fuse_topk call launches: select + merge, + block maxima and bound when the shard is large enough
+        for a starting bound (the rule of fuse_topk_impl in csrc/topk.cu)."""
+        if n <= 0:
+            return 0
+        bound = any(n >= nb * 128 * 2 and k <= nb // 2 for nb in (1024, 512, 256))
+        return 4 if bound else 2
 
     def _merge_across(self, keys: torch.Tensor) -> torch.Tensor:
         """C1: all-gather of the per-shard key lists [B, k] + merge kernel; identity on a single shard."""
@@ -569,7 +578,7 @@ class SearchEngine:
             check(self.lib.hs_fuse_topk_f16(self.shard.handle, mode, ptr(cos), ptr(b), 1 if b_half else 0, cos.stride(0),
                                             ptr(stats), float(wa), float(wb), nb, k_sel, ptr(ws), ws_bytes, ptr(approx), st),
                   "hs_fuse_topk_f16")
-            self.launches += 2
+            self.launches += self._select_launches(n, k_sel)
         else:
             approx = self.fuse_topk(mode, cos, b, stats, wa, wb, k_sel, merge=False, out="vkeys")
         mark("select")
